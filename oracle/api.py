@@ -1,0 +1,592 @@
+"""Oracle restatement of the reference's Python API for the hot path, on pyarrow
+Tables, returning pandas DataFrames with the reference's column names.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Follows (relative to /root/reference/src/main/anovos):
+  data_analyzer/stats_generator.py:33-1011
+  data_transformer/transformers.py:87-291   (attribute_binning)
+  drift_stability/drift_detector.py:16-371  (statistics)
+  drift_stability/validations.py:8-94
+  shared/utils.py:28-73
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+
+import numpy as np
+import pandas as pd
+import pyarrow as pa
+
+from . import spark_semantics as S
+
+R = S.round_half_up
+
+
+def table_from_rows(rows, names) -> pa.Table:
+    """spark.createDataFrame(rows, names) analogue used by the ported reference tests:
+    python int -> bigint, float -> double, str -> string, None -> null."""
+    cols = list(zip(*rows)) if rows else [[] for _ in names]
+    arrays = []
+    for c in cols:
+        non_null = [v for v in c if v is not None]
+        if non_null and all(isinstance(v, str) for v in non_null):
+            arrays.append(pa.array(list(c), type=pa.string()))
+        elif non_null and all(isinstance(v, (int, np.integer)) and not isinstance(v, bool) for v in non_null):
+            arrays.append(pa.array(list(c), type=pa.int64()))
+        else:
+            arrays.append(pa.array(list(c), type=pa.float64()))
+    return pa.table(arrays, names=list(names))
+
+
+# ---------------------------------------------------------------------------
+# argument normalisation (stats_generator.py:295-307 idiom)
+# ---------------------------------------------------------------------------
+
+
+def _split(x):
+    if isinstance(x, str):
+        return [s.strip() for s in x.split("|")]
+    return list(x)
+
+
+def _dedupe(cols, drop):
+    out = []
+    for c in cols:
+        if c not in drop and c not in out:
+            out.append(c)
+    return out  # reference: list(set(...)) - order arbitrary, we keep input order
+
+
+def _resolve(table, list_of_cols, drop_cols, default, universe=None, allow_empty=False):
+    if isinstance(list_of_cols, str) and list_of_cols == "all":
+        list_of_cols = default
+    cols = _dedupe(_split(list_of_cols), _split(drop_cols))
+    universe = table.column_names if universe is None else universe
+    if any(c not in universe for c in cols) or (len(cols) == 0 and not allow_empty):
+        raise TypeError("Invalid input for Column(s)")
+    return cols
+
+
+class ColumnProfile:
+    """Everything the stats functions need from one column (float64 semantics)."""
+
+    def __init__(self, table, name):
+        self.name = name
+        self.sdtype = S.spark_dtype(table.schema.field(name).type)
+        vals, valid = S.column_values(table, name)
+        self.N = len(vals)
+        self.valid = valid
+        self.values = vals
+        self.nn = vals[valid]
+        self.n = int(self.nn.size)
+        self.is_num = self.sdtype in ("double", "int", "bigint", "float", "long") or self.sdtype.startswith("decimal")
+        self._x64 = None
+        self._sorted = None
+
+    @property
+    def x64(self):
+        if self._x64 is None:
+            self._x64 = self.nn.astype(np.float64)
+        return self._x64
+
+    @property
+    def sorted64(self):
+        if self._sorted is None:
+            self._sorted = np.sort(self.x64, kind="stable")
+        return self._sorted
+
+    def _disp(self, v):
+        """summary() string round trip for float32 min/max/percentiles."""
+        if v is None:
+            return None
+        if self.sdtype == "float":
+            return S.float32_via_string(v)
+        return float(v)
+
+    def minmax(self):
+        if self.n == 0:
+            return None, None
+        x = self.x64
+        if np.isnan(x).any():  # Spark: NaN is the largest value (unpinned)
+            nn = x[~np.isnan(x)]
+            return (float(nn.min()) if nn.size else float("nan")), float("nan")
+        return float(x.min()), float(x.max())
+
+    def quantile(self, p):
+        if self.n == 0:
+            return None
+        return float(S.quantile_sorted(self.sorted64, p))
+
+    def nonzero(self):
+        if self.n == 0:
+            return 0
+        return int(np.count_nonzero(self.x64 != 0))
+
+    def mode(self):
+        """-> (mode value, rows) over non-null values; ties arbitrary (first in sort
+        order here).  stats_generator.py:386-401."""
+        if self.n == 0:
+            return None, None
+        if self.sdtype == "string":
+            u, c = np.unique(self.nn.astype(str), return_counts=True)
+        else:
+            u, c = np.unique(self.nn, return_counts=True)
+        i = int(np.argmax(c))
+        return u[i], int(c[i])
+
+    def distinct(self):
+        if self.n == 0:
+            return 0
+        if self.sdtype == "string":
+            return int(len(set(self.nn.tolist())))
+        x = self.nn
+        if x.dtype.kind == "f":
+            x = x.copy()
+            x[x == 0] = 0.0
+        return int(np.unique(x).size)
+
+
+def _profiles(table, cols):
+    return {c: ColumnProfile(table, c) for c in cols}
+
+
+# ---------------------------------------------------------------------------
+# stats_generator
+# ---------------------------------------------------------------------------
+
+
+def global_summary(table, list_of_cols="all", drop_cols=[]):
+    """stats_generator.py:33-113."""
+    cols = _resolve(table, list_of_cols, drop_cols, table.column_names)
+    num, cat, other = S.segregate(table.select(cols))
+    rows = [["rows_count", str(table.num_rows)], ["columns_count", str(len(cols))],
+            ["numcols_count", str(len(num))], ["numcols_name", ", ".join(num)],
+            ["catcols_count", str(len(cat))], ["catcols_name", ", ".join(cat)],
+            ["othercols_count", str(len(other))], ["othercols_name", ", ".join(other)]]
+    return pd.DataFrame(rows, columns=["metric", "value"])
+
+
+def missingCount_computation(table, list_of_cols="all", drop_cols=[]):
+    """stats_generator.py:116-176."""
+    num, cat, _ = S.segregate(table)
+    cols = _resolve(table, list_of_cols, drop_cols, num + cat)
+    N = table.num_rows
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        miss = N - p.n
+        rows.append([c, miss, R(miss / N) if N else None])
+    return pd.DataFrame(rows, columns=["attribute", "missing_count", "missing_pct"])
+
+
+def nonzeroCount_computation(table, list_of_cols="all", drop_cols=[]):
+    """stats_generator.py:179-248 (MLlib colStats.numNonzeros after fillna(0))."""
+    num = S.segregate(table)[0]
+    cols = _resolve(table, list_of_cols, drop_cols, num, universe=num, allow_empty=True)
+    if not cols:
+        warnings.warn("No Non-Zero Count Computation - No numerical column(s) to analyze")
+        return pd.DataFrame(columns=["attribute", "nonzero_count", "nonzero_pct"])
+    N = table.num_rows
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        nz = p.nonzero()
+        rows.append([c, nz, R(nz / N)])
+    return pd.DataFrame(rows, columns=["attribute", "nonzero_count", "nonzero_pct"])
+
+
+def measures_of_counts(table, list_of_cols="all", drop_cols=[]):
+    """stats_generator.py:251-325."""
+    num, cat, _ = S.segregate(table)
+    cols = _resolve(table, list_of_cols, drop_cols, num + cat)
+    num_sel = S.segregate(table.select(cols))[0]
+    N = table.num_rows
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        fill_pct = R(p.n / N)
+        row = [c, p.n, fill_pct, N - p.n, R(1 - fill_pct)]       # :313-319
+        if c in num_sel:
+            nz = p.nonzero()
+            row += [nz, R(nz / N)]
+        else:
+            row += [None, None]
+        rows.append(row)
+    return pd.DataFrame(rows, columns=["attribute", "fill_count", "fill_pct", "missing_count",
+                                       "missing_pct", "nonzero_count", "nonzero_pct"])
+
+
+def mode_computation(table, list_of_cols="all", drop_cols=[]):
+    """stats_generator.py:328-421."""
+    num, cat, _ = S.segregate(table)
+    cols = _resolve(table, list_of_cols, drop_cols, num + cat, allow_empty=True)
+    if not cols:
+        warnings.warn("No Mode Computation - No discrete column(s) to analyze")
+        return pd.DataFrame(columns=["attribute", "mode", "mode_rows"])
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        m, r = p.mode()
+        if m is None:
+            continue  # all-null column: groupBy on empty frame yields no row (:386-401)
+        rows.append([c, S.mode_to_string(m, p.sdtype), r])
+    return pd.DataFrame(rows, columns=["attribute", "mode", "mode_rows"])
+
+
+def measures_of_centralTendency(table, list_of_cols="all", drop_cols=[], raw=False):
+    """stats_generator.py:424-526.  raw=True skips the round(...,4)."""
+    num, cat, _ = S.segregate(table)
+    cols = _resolve(table, list_of_cols, drop_cols, num + cat)
+    rnd = (lambda v: v) if raw else R
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        mean = median = None
+        if c in num and p.n:
+            mean = rnd(S.central_moments(p.x64)[1])
+            median = rnd(p._disp(p.quantile(0.5)))
+        m, r = p.mode()
+        rows.append([c, mean, median, None if m is None else S.mode_to_string(m, p.sdtype), r,
+                     None if r is None else rnd(r / p.n)])
+    return pd.DataFrame(rows, columns=["attribute", "mean", "median", "mode", "mode_rows", "mode_pct"])
+
+
+def uniqueCount_computation(table, list_of_cols="all", drop_cols=[], compute_approx_unique_count=False,
+                            rsd=None, with_flags=False):
+    """stats_generator.py:529-620."""
+    num, cat, _ = S.segregate(table)
+    cols = _resolve(table, list_of_cols, drop_cols, num + cat, allow_empty=True)
+    if rsd is not None and rsd < 0:
+        raise ValueError("rsd value can not be less than 0 (default value is 0.05)")
+    if not cols:
+        warnings.warn("No Unique Count Computation - No discrete column(s) to analyze")
+        return pd.DataFrame(columns=["attribute", "unique_values"])
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        if compute_approx_unique_count:
+            est, band = S.approx_count_distinct(p.nn, p.sdtype, rsd)
+            if band:  # HLL++ bias-correction band: tables unavailable offline -> exact distinct,
+                est = p.distinct()  # row flagged "HLL bias band, parity unpinned" 
+            rows.append([c, est, band])
+        else:
+            rows.append([c, p.distinct(), False])
+    df = pd.DataFrame(rows, columns=["attribute", "unique_values", "hll_bias_band"])
+    return df if with_flags else df[["attribute", "unique_values"]]
+
+
+def measures_of_cardinality(table, list_of_cols="all", drop_cols=[], use_approx_unique_count=True, rsd=None,
+                            with_flags=False):
+    """stats_generator.py:623-733."""
+    num, cat, _ = S.segregate(table)
+    cols = _resolve(table, list_of_cols, drop_cols, num + cat, allow_empty=True)
+    if rsd is not None and rsd < 0:
+        raise ValueError("rsd value can not be less than 0 (default value is 0.05)")
+    if not cols:
+        warnings.warn("No Cardinality Computation - No discrete column(s) to analyze")
+        return pd.DataFrame(columns=["attribute", "unique_values", "IDness"])
+    u = uniqueCount_computation(table, cols, compute_approx_unique_count=use_approx_unique_count, rsd=rsd,
+                                with_flags=True)
+    N = table.num_rows
+    profs = _profiles(table, cols)
+    idn = []
+    for c, uv in zip(u["attribute"], u["unique_values"]):
+        denom = N - (N - profs[c].n)
+        idn.append(R(uv / denom) if denom else None)     # x/0 -> null in Spark SQL
+    u["IDness"] = idn
+    return u if with_flags else u[["attribute", "unique_values", "IDness"]]
+
+
+def measures_of_dispersion(table, list_of_cols="all", drop_cols=[], raw=False):
+    """stats_generator.py:736-829.  raw=True: unrounded stddev/variance/cov/IQR/range
+    (variance = stddev^2 without the intermediate rounding)."""
+    num = S.segregate(table)[0]
+    cols = _resolve(table, list_of_cols, drop_cols, num, universe=num, allow_empty=True)
+    if not cols:
+        warnings.warn("No Dispersion Computation - No numerical column(s) to analyze")
+        return pd.DataFrame(columns=["attribute", "stddev", "variance", "cov", "IQR", "range"])
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        if p.n == 0:
+            rows.append([c, None, None, None, None, None])
+            continue
+        n, mean, m2, _, _ = S.central_moments(p.x64)
+        sd = S.stddev_samp(n, m2)
+        mn, mx = p.minmax()
+        q25, q75 = p._disp(p.quantile(0.25)), p._disp(p.quantile(0.75))
+        mn, mx = p._disp(mn), p._disp(mx)
+        if raw:
+            rows.append([c, sd, None if sd is None else sd * sd, None if sd is None else sd / mean,
+                         q75 - q25, mx - mn])
+            continue
+        sd_r = R(sd)                                                           # :818
+        var = None if sd_r is None else R(sd_r * sd_r)                         # :819
+        rng = R(mx - mn)                                                       # :820
+        if sd_r is None:
+            cov = None
+        elif mean == 0:
+            cov = None  # Spark SQL: division by zero -> null
+        else:
+            cov = R(sd_r / mean)                                               # :821
+        rows.append([c, sd_r, var, cov, R(q75 - q25), rng])                    # :822
+    return pd.DataFrame(rows, columns=["attribute", "stddev", "variance", "cov", "IQR", "range"])
+
+
+PCT_STATS = ["min", "1%", "5%", "10%", "25%", "50%", "75%", "90%", "95%", "99%", "max"]
+
+
+def measures_of_percentiles(table, list_of_cols="all", drop_cols=[], raw=False):
+    """stats_generator.py:832-916."""
+    num = S.segregate(table)[0]
+    cols = _resolve(table, list_of_cols, drop_cols, num, universe=num, allow_empty=True)
+    if not cols:
+        warnings.warn("No Percentiles Computation - No numerical column(s) to analyze")
+        return pd.DataFrame(columns=["attribute"] + PCT_STATS)
+    rnd = (lambda v: v) if raw else R
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        if p.n == 0:
+            rows.append([c] + [None] * 11)
+            continue
+        mn, mx = p.minmax()
+        row = [c, rnd(p._disp(mn))]
+        for s in PCT_STATS[1:-1]:
+            row.append(rnd(p._disp(p.quantile(S.SUMMARY_PCTS[s]))))
+        row.append(rnd(p._disp(mx)))
+        rows.append(row)
+    return pd.DataFrame(rows, columns=["attribute"] + PCT_STATS)
+
+
+def measures_of_shape(table, list_of_cols="all", drop_cols=[], raw=False):
+    """stats_generator.py:919-1011."""
+    num = S.segregate(table)[0]
+    cols = _resolve(table, list_of_cols, drop_cols, num, universe=num, allow_empty=True)
+    if not cols:
+        warnings.warn("No Skewness/Kurtosis Computation - No numerical column(s) to analyze")
+        return pd.DataFrame(columns=["attribute", "skewness", "kurtosis"])
+    rnd = (lambda v: v) if raw else R
+    rows = []
+    for c, p in _profiles(table, cols).items():
+        n, mean, m2, m3, m4 = S.central_moments(p.x64)
+        rows.append([c, rnd(S.skewness(n, m2, m3)), rnd(S.kurtosis(n, m2, m4))])
+    return pd.DataFrame(rows, columns=["attribute", "skewness", "kurtosis"])
+
+
+# ---------------------------------------------------------------------------
+# attribute_binning (transformers.py:87-291)
+# ---------------------------------------------------------------------------
+
+
+def binning_cutoffs(table, cols, method_type="equal_range", bin_size=10):
+    """-> (kept cols, cutoffs list-of-lists) following transformers.py:210-240."""
+    kept, cuts, dropped = [], [], []
+    for c in cols:
+        p = ColumnProfile(table, c)
+        if method_type == "equal_frequency":
+            if p.n == 0:
+                kept.append(c)
+                cuts.append([float("nan")] * (bin_size - 1))  # approxQuantile on empty: unpinned
+                continue
+            kept.append(c)
+            cuts.append(S.equal_frequency_cutoffs(p.sorted64, bin_size))
+        else:
+            if p.n == 0:
+                dropped.append(c)                       # :226-228
+                continue
+            mn, mx = p.minmax()
+            kept.append(c)
+            cuts.append(S.equal_range_cutoffs(mn, mx, bin_size))
+    if dropped:
+        warnings.warn("Columns contains too much null values. Dropping " + ", ".join(dropped))
+    return kept, cuts
+
+
+def _write_model(model_path, cols, cuts):
+    import pyarrow.parquet as pq
+    d = os.path.join(model_path, "attribute_binning")
+    os.makedirs(d, exist_ok=True)
+    t = pa.table({"attribute": pa.array(cols, pa.string()),
+                  "parameters": pa.array(cuts, pa.list_(pa.float64()))})
+    pq.write_table(t, os.path.join(d, "part-00000.parquet"))
+
+
+def _read_model(model_path):
+    import pyarrow.parquet as pq
+    t = pq.read_table(os.path.join(model_path, "attribute_binning"))
+    return dict(zip(t.column("attribute").to_pylist(), t.column("parameters").to_pylist()))
+
+
+def attribute_binning(table, list_of_cols="all", drop_cols=[], method_type="equal_range", bin_size=10,
+                      bin_dtype="numerical", pre_existing_model=False, model_path="NA", output_mode="replace"):
+    """transformers.py:87-291 -> pyarrow Table with int32 bin ids (null stays null)."""
+    num = S.segregate(table)[0]
+    cols = _resolve(table, list_of_cols, drop_cols, num, universe=num, allow_empty=True)
+    if not cols:
+        warnings.warn("No Binning Performed - No numerical column(s) to transform")
+        return table
+    if method_type not in ("equal_frequency", "equal_range"):
+        raise TypeError("Invalid input for method_type")
+    if bin_size < 2:
+        raise TypeError("Invalid input for bin_size")
+    if output_mode not in ("replace", "append"):
+        raise TypeError("Invalid input for output_mode")
+    if pre_existing_model:
+        model = _read_model(model_path)
+        cuts = []
+        for c in cols:
+            if c not in model:
+                raise IndexError("list index out of range")      # test_transformers.py:63-73
+            cuts.append(model[c])
+    else:
+        cols, cuts = binning_cutoffs(table, cols, method_type, bin_size)
+        if model_path != "NA":
+            _write_model(model_path, cols, cuts)
+    out = table
+    n_over = (len(cuts[0]) + 1) if cuts else bin_size            # :269 quirk (Appendix C #3)
+    for c, cut in zip(cols, cuts):
+        p = ColumnProfile(table, c)
+        x = p.values.astype(np.float64)
+        ids = S.assign_bins(x, p.valid, cut, bin_size)
+        ids[(ids == len(cut) + 1)] = n_over
+        if bin_dtype == "numerical":
+            arr = pa.array(ids, type=pa.int32(), mask=~p.valid)
+        else:
+            labels = []
+            for k, ok in zip(ids.tolist(), p.valid.tolist()):
+                if not ok:
+                    labels.append(None)
+                elif k == 1:
+                    labels.append("<= " + str(round(cut[0], 4)))
+                elif k <= len(cut):
+                    labels.append(str(round(cut[k - 2], 4)) + "-" + str(round(cut[k - 1], 4)))
+                else:
+                    labels.append("> " + str(round(cut[len(cuts[0]) - 1], 4)))
+            arr = pa.array(labels, type=pa.string())
+        if output_mode == "replace":
+            out = out.set_column(out.column_names.index(c), c, arr)
+        else:
+            out = out.append_column(c + "_binned", arr)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# drift_detector.statistics (drift_detector.py:16-371)
+# ---------------------------------------------------------------------------
+
+
+def _check_columns(table, list_of_cols, drop_cols):
+    """validations.py:19-66."""
+    if isinstance(list_of_cols, str):
+        if list_of_cols == "all":
+            num, cat, _ = S.segregate(table)
+            cols = num + cat
+        else:
+            cols = [x.strip() for x in list_of_cols.split("|")]
+    elif isinstance(list_of_cols, list):
+        cols = list_of_cols
+    else:
+        raise TypeError("'list_of_cols' must be either a string or a list of strings. Received %s." % type(list_of_cols))
+    if drop_cols is None:
+        drop_cols = []
+    if isinstance(drop_cols, str):
+        drops = [x.strip() for x in drop_cols.split("|")]
+    elif isinstance(drop_cols, list):
+        drops = drop_cols
+    else:
+        raise TypeError("'drop_cols' must be either a string or a list of strings. Received %s." % type(drop_cols))
+    final = _dedupe(cols, drops)
+    if not final:
+        raise ValueError("Empty set of columns is given. Columns to select: %s, columns to drop: %s." % (cols, drops))
+    if any(c not in table.column_names for c in final):
+        raise ValueError("Not all columns are in the input dataframe. Missing columns: %s"
+                         % (set(final) - set(table.column_names)))
+    return final
+
+
+def _check_methods(method_type):
+    """validations.py:71-94."""
+    m = method_type
+    if isinstance(m, str):
+        m = ["PSI", "JSD", "HD", "KS"] if m == "all" else [x.strip() for x in m.split("|")]
+    if any(x not in ("PSI", "JSD", "HD", "KS") for x in m):
+        raise TypeError("Invalid input for method_type")
+    return m
+
+
+def _group_counts(table, col, is_binned_numeric):
+    """groupBy(col).agg(count(col)): dict key -> non-null count; null group -> key -1
+    (numeric, after fillna(-1)) or dropped from matching (string: SQL null never joins)."""
+    vals, valid = S.column_values(table, col)
+    groups = {}
+    if valid.any():
+        nn = vals[valid]
+        if nn.dtype == object:
+            u, c = np.unique(nn.astype(str), return_counts=True)
+            u = u.tolist()
+        else:
+            u, c = np.unique(nn, return_counts=True)
+            u = u.tolist()
+        for k, v in zip(u, c.tolist()):
+            groups[k] = int(v)
+    if (~valid).any() and is_binned_numeric:
+        groups[-1] = 0
+    return groups
+
+
+def statistics(idf_target, idf_source, *, list_of_cols="all", drop_cols=None, method_type="PSI",
+               bin_method="equal_range", bin_size=10, threshold=0.1, use_sampling=True, sample_size=100000,
+               pre_existing_source=False, source_save=True, source_path="NA",
+               model_directory="drift_statistics", return_groups=False):
+    """drift_detector.py:16-371.  Sampling (:187-211) is not restated: callers must
+    keep both frames <= sample_size or pass use_sampling=False (Spark Bernoulli
+    sampling is RNG-dependent: parity unpinned)."""
+    cols = _check_columns(idf_target, list_of_cols, drop_cols)
+    methods = _check_methods(method_type)
+    num_cols = S.segregate(idf_target.select(cols))[0]
+    n_t, n_s = idf_target.num_rows, (idf_source.num_rows if idf_source is not None else None)
+    if use_sampling and (n_t > sample_size or (n_s or 0) > sample_size):
+        raise NotImplementedError("oracle: Bernoulli sampling is not restated (parity unpinned)")
+    if source_path == "NA":
+        source_path = "intermediate_data"
+    model_path = source_path + "/" + model_directory
+    if not pre_existing_source:
+        source_bin = attribute_binning(idf_source, list_of_cols=num_cols, method_type=bin_method,
+                                       bin_size=bin_size, pre_existing_model=False, model_path=model_path) \
+            if num_cols else idf_source
+    # equal_range drops all-null source columns from the model: the target then keeps raw values
+    model = _read_model(model_path) if num_cols else {}
+    tgt_num = [c for c in num_cols if c in model]
+    target_bin = attribute_binning(idf_target, list_of_cols=tgt_num, method_type=bin_method, bin_size=bin_size,
+                                   pre_existing_model=True, model_path=model_path) if tgt_num else idf_target
+    rows, dbg = [], {}
+    for c in cols:
+        binned = c in num_cols
+        if pre_existing_source:
+            f = pd.read_csv(os.path.join(model_path, "frequency_counts", c, "part-00000.csv"))
+            src = {k: v for k, v in zip(f[c].tolist(), f["p"].tolist())}
+            src_p_direct = True
+        else:
+            src = _group_counts(source_bin, c, binned)
+            src_p_direct = False
+            if source_save:
+                d = os.path.join(model_path, "frequency_counts", c)
+                os.makedirs(d, exist_ok=True)
+                keys = sorted(src, key=lambda k: (k is None, k))
+                pd.DataFrame({c: keys, "p": [src[k] / n_s for k in keys]}).to_csv(
+                    os.path.join(d, "part-00000.csv"), index=False)
+        tgt = _group_counts(target_bin, c, binned)
+        keys = sorted(set(src) | set(tgt))
+        if src_p_direct:
+            # p comes from the saved CSV (drift_detector.py:245-250): already proportions
+            tgt_p = {k: v / n_t for k, v in tgt.items()}
+            psi, hd, jsd, ks = S.drift_from_groups(src, tgt_p, 1, 1, keys)
+        else:
+            psi, hd, jsd, ks = S.drift_from_groups(src, tgt, n_s, n_t, keys)
+        if psi is None:
+            psi = hd = jsd = ks = None
+        row = {"attribute": c}
+        for name, v in (("PSI", psi), ("HD", hd), ("JSD", jsd), ("KS", ks)):   # code order :273-335
+            if name in methods:
+                row[name] = v
+        vals = [row[m] for m in row if m != "attribute"]
+        row["flagged"] = int(any(v is not None and v > threshold for v in vals))  # :353-356
+        rows.append(row)
+        dbg[c] = (src, tgt)
+    out = pd.DataFrame(rows)
+    return (out, dbg) if return_groups else out
