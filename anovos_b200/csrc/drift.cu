@@ -1,0 +1,81 @@
+// K3: drift reduce.  One thread per column walks the (p, q) table in key order
+// exactly like the reference's orderBy(i) + sum / window aggregations
+// (/root/reference/src/main/anovos/drift_stability/drift_detector.py:266-335):
+// fillna(1e-4) for a key missing on one side, replace(0 -> 1e-4), then
+// PSI = sum (p-q) ln(p/q), HD = sqrt(sum (sqrt p - sqrt q)^2 / 2),
+// JSD = (sum p ln(p/m) + sum q ln(q/m)) / 2 with m = (p+q)/2, KS = max |cum p - cum q|.
+// Everything in FP64, sequential per column: bit-reproducible.
+#include "common.cuh"
+
+namespace anv {
+
+struct DriftAcc {
+  double psi = 0, hd = 0, pm = 0, qm = 0, cp = 0, cq = 0, ks = 0;
+  int rows = 0;
+  __device__ __forceinline__ void row(double p, double q) {
+    if (p == 0.0) p = 0.0001;
+    if (q == 0.0) q = 0.0001;
+    psi += (p - q) * log(p / q);
+    const double t = sqrt(p) - sqrt(q);
+    hd += t * t;
+    const double m = (p + q) / 2;
+    pm += p * log(p / m);
+    qm += q * log(q / m);
+    cp += p;
+    cq += q;
+    ks = fmax(ks, fabs(cp - cq));
+    ++rows;
+  }
+};
+
+__global__ void drift_reduce_kernel(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ tgt,
+                                    const double* __restrict__ src_p, int src_is_p, const int32_t* __restrict__ n_slots,
+                                    const int32_t* __restrict__ kind, int n_cols, int stride, double n_src, double n_tgt,
+                                    anv_drift_t* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  const unsigned long long* t = tgt + (size_t)c * stride;
+  const unsigned long long* s = src_is_p ? nullptr : src + (size_t)c * stride;
+  const double* sp = src_is_p ? src_p + (size_t)c * stride : nullptr;
+  const int ns = n_slots[c];
+  DriftAcc a;
+  // slot 0: the null group.  count(col) of a null group is 0 -> p (or q) = 0 -> 1e-4.
+  const bool s_null = src_is_p ? !isnan(sp[0]) : (s[0] > 0);
+  const bool t_null = t[0] > 0;
+  if (kind[c] == 0) {  // binned numeric: fillna(-1) makes the null groups join on key -1 (:252-256,264)
+    if (s_null || t_null) a.row(0.0001, 0.0001);
+  } else {             // string keys stay SQL NULL and never match in the full outer join (:266)
+    if (s_null) a.row(0.0001, 0.0001);
+    if (t_null) a.row(0.0001, 0.0001);
+  }
+  for (int k = 1; k < ns; ++k) {
+    bool ps, pt = t[k] > 0;
+    double p, q = pt ? (double)t[k] / n_tgt : 0.0001;
+    if (src_is_p) { ps = !isnan(sp[k]); p = ps ? sp[k] : 0.0001; }
+    else { ps = s[k] > 0; p = ps ? (double)s[k] / n_src : 0.0001; }
+    if (ps || pt) a.row(p, q);
+  }
+  anv_drift_t r;
+  r.n_rows = a.rows; r.reserved = 0;
+  if (a.rows) { r.psi = a.psi; r.hd = sqrt(a.hd / 2); r.jsd = (a.pm + a.qm) / 2; r.ks = a.ks; }
+  else { r.psi = r.hd = r.jsd = r.ks = nan(""); }
+  out[c] = r;
+}
+
+}  // namespace anv
+
+extern "C" int anv_drift_reduce(const uint64_t* src_counts, const uint64_t* tgt_counts, const double* src_p, int src_is_p,
+                                const int32_t* n_slots, const int32_t* kind, int n_cols, int count_stride, int64_t n_src,
+                                int64_t n_tgt, anv_drift_t* out, void* stream) {
+  if (n_cols < 0) { anv::set_error("anv_drift_reduce: negative n_cols"); return ANV_ERR_INVALID; }
+  if (n_cols == 0) return ANV_OK;
+  if (!tgt_counts || !n_slots || !kind || !out || (src_is_p ? !src_p : !src_counts)) {
+    anv::set_error("anv_drift_reduce: NULL argument");
+    return ANV_ERR_INVALID;
+  }
+  anv::drift_reduce_kernel<<<(n_cols + 31) / 32, 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(src_counts), reinterpret_cast<const unsigned long long*>(tgt_counts),
+      src_p, src_is_p, n_slots, kind, n_cols, count_stride, (double)n_src, (double)n_tgt, out);
+  ANV_CUDA(cudaGetLastError());
+  return ANV_OK;
+}

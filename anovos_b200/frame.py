@@ -1,0 +1,290 @@
+"""Columnar frame: the `idf` of the B200 path.
+
+The reference passes Spark DataFrames (`idf`) into every function of the hot path;
+here `idf` is a ColumnFrame: column-major device buffers (one contiguous torch CUDA
+tensor per column + optional Arrow validity bitmap), dictionary codes for string
+columns, and the Spark dtype string of every column so that
+`attributeType_segregation` (reference shared/utils.py:48-73) behaves identically.
+
+`as_frame(x)` accepts a ColumnFrame, a pyarrow Table, a pandas DataFrame or a dict of
+torch tensors / numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+
+_NUMERIC_SPARK = ("double", "int", "bigint", "float", "long")
+
+
+def spark_dtype_of_arrow(t) -> str:
+    """Arrow type -> Spark SQL dtype string as `idf.dtypes` would print it."""
+    import pyarrow as pa
+    if pa.types.is_dictionary(t):
+        return spark_dtype_of_arrow(t.value_type)
+    if pa.types.is_string(t) or pa.types.is_large_string(t):
+        return "string"
+    if pa.types.is_int32(t):
+        return "int"
+    if pa.types.is_int64(t) or pa.types.is_uint32(t):
+        return "bigint"
+    if pa.types.is_float32(t):
+        return "float"
+    if pa.types.is_float64(t):
+        return "double"
+    if pa.types.is_decimal(t):
+        return "decimal(%d,%d)" % (t.precision, t.scale)
+    if pa.types.is_int16(t) or pa.types.is_uint8(t):
+        return "smallint"
+    if pa.types.is_int8(t):
+        return "tinyint"
+    if pa.types.is_boolean(t):
+        return "boolean"
+    if pa.types.is_date(t):
+        return "date"
+    if pa.types.is_timestamp(t):
+        return "timestamp"
+    if pa.types.is_null(t):
+        return "void"
+    return str(t)
+
+
+def kind_of(sdtype: str) -> str:
+    """'num' | 'cat' | 'other' exactly as shared/utils.py:64-72 decides."""
+    if sdtype == "string":
+        return "cat"
+    if sdtype in _NUMERIC_SPARK or sdtype.startswith("decimal"):
+        return "num"
+    return "other"
+
+
+_NP_TO_ANV = {np.dtype("float32"): (_lib.ANV_F32, "float"), np.dtype("float64"): (_lib.ANV_F64, "double"),
+              np.dtype("int32"): (_lib.ANV_I32, "int"), np.dtype("int64"): (_lib.ANV_I64, "bigint")}
+
+
+def _pack_validity(valid_bool: np.ndarray) -> np.ndarray:
+    """bool[n] -> Arrow LSB-first bitmap as int32 words (padded with zeros)."""
+    bits = np.packbits(valid_bool, bitorder="little")
+    pad = (-len(bits)) % 4
+    if pad:
+        bits = np.concatenate([bits, np.zeros(pad, np.uint8)])
+    return bits.view(np.int32)
+
+
+def _arrow_validity_words(arr):
+    """Arrow array -> int32 bitmap words (None when the array has no nulls)."""
+    if arr.null_count == 0:
+        return None
+    n = len(arr)
+    buf = arr.buffers()[0]
+    if buf is not None and arr.offset == 0:
+        nbytes = (n + 7) // 8
+        raw = np.frombuffer(buf, dtype=np.uint8, count=nbytes).copy()
+        if n % 8:
+            raw[-1] &= (1 << (n % 8)) - 1  # bits past n_rows must read as 0
+        pad = (-len(raw)) % 4
+        if pad:
+            raw = np.concatenate([raw, np.zeros(pad, np.uint8)])
+        return raw.view(np.int32)
+    return _pack_validity(np.asarray(arr.is_valid()))
+
+
+class Column:
+    __slots__ = ("name", "sdtype", "kind", "anv_dtype", "n_rows", "null_count", "dictionary",
+                 "_host", "_host_valid", "_dev", "_dev_valid")
+
+    def __init__(self, name, sdtype, n_rows, host=None, host_valid=None, dev=None, dev_valid=None,
+                 anv_dtype=None, null_count=None, dictionary=None):
+        self.name, self.sdtype, self.kind = name, sdtype, kind_of(sdtype)
+        self.n_rows = int(n_rows)
+        self._host, self._host_valid, self._dev, self._dev_valid = host, host_valid, dev, dev_valid
+        self.anv_dtype = anv_dtype
+        self.null_count = null_count
+        self.dictionary = dictionary
+
+    @property
+    def has_validity(self):
+        return self._host_valid is not None or self._dev_valid is not None
+
+    def device(self):
+        """-> (data tensor, validity tensor|None) on the current CUDA device (uploads once)."""
+        torch = _lib.require_cuda()
+        if self.kind == "other":
+            raise _lib.AnvError("column %r has dtype %s which the hot path does not process" % (self.name, self.sdtype))
+        if self._dev is None:
+            t = torch.from_numpy(self._host)
+            self._dev = t.cuda(non_blocking=False)
+            if self._host_valid is not None:
+                self._dev_valid = torch.from_numpy(self._host_valid).cuda(non_blocking=False)
+        return self._dev, self._dev_valid
+
+    def drop_device(self):
+        if self._host is not None:
+            self._dev = self._dev_valid = None
+
+
+class ColumnFrame:
+    """Immutable column-major frame; `columns` / `dtypes` / `count()` mirror the Spark API
+    the reference uses."""
+
+    def __init__(self, cols: "OrderedDict[str, Column]", n_rows: int):
+        self._cols = cols
+        self.n_rows = int(n_rows)
+        self._cache = {}
+
+    # ---- Spark-DataFrame-like surface used by the reference code ------------------------
+    @property
+    def columns(self):
+        return list(self._cols)
+
+    @property
+    def dtypes(self):
+        return [(c.name, c.sdtype) for c in self._cols.values()]
+
+    def count(self):
+        return self.n_rows
+
+    def select(self, names):
+        if isinstance(names, str):
+            names = [names]
+        return ColumnFrame(OrderedDict((n, self._cols[n]) for n in names), self.n_rows)
+
+    def column(self, name) -> Column:
+        return self._cols[name]
+
+    def __contains__(self, name):
+        return name in self._cols
+
+    # ---- constructors -----------------------------------------------------------------
+    @staticmethod
+    def from_arrow(table) -> "ColumnFrame":
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        cols = OrderedDict()
+        n = table.num_rows
+        for field in table.schema:
+            arr = table.column(field.name)
+            arr = arr.combine_chunks() if arr.num_chunks != 1 else arr.chunk(0)
+            if isinstance(arr, pa.ChunkedArray):  # zero chunks
+                arr = pa.array([], type=field.type)
+            t = arr.type
+            sd = spark_dtype_of_arrow(t)
+            k = kind_of(sd)
+            if k == "other":
+                cols[field.name] = Column(field.name, sd, n)
+                continue
+            if k == "cat":
+                if not pa.types.is_dictionary(t):
+                    arr = pc.dictionary_encode(arr)
+                dic = arr.dictionary.to_pylist()
+                idx = arr.indices
+                codes = (idx.fill_null(0) if idx.null_count else idx).to_numpy(zero_copy_only=False).astype(np.int32)
+                order = sorted(range(len(dic)), key=lambda i: dic[i].encode("utf-8"))  # Spark: UTF-8 byte order
+                remap = np.empty(max(len(dic), 1), dtype=np.int32)
+                remap[np.asarray(order, dtype=np.int64)] = np.arange(len(dic), dtype=np.int32)
+                codes = remap[codes] if len(dic) else codes
+                cols[field.name] = Column(field.name, "string", n, host=np.ascontiguousarray(codes),
+                                          host_valid=_arrow_validity_words(idx), anv_dtype=_lib.ANV_I32,
+                                          null_count=idx.null_count, dictionary=[dic[i] for i in order])
+                continue
+            if pa.types.is_decimal(t):
+                arr = arr.cast(pa.float64())
+            elif pa.types.is_uint32(t):
+                arr = arr.cast(pa.int64())
+            vals = (arr.fill_null(0) if arr.null_count else arr).to_numpy(zero_copy_only=False)
+            vals = np.ascontiguousarray(vals)
+            anv_dt = _NP_TO_ANV[vals.dtype][0]
+            cols[field.name] = Column(field.name, sd, n, host=vals, host_valid=_arrow_validity_words(arr),
+                                      anv_dtype=anv_dt, null_count=arr.null_count)
+        return ColumnFrame(cols, n)
+
+    @staticmethod
+    def from_pandas(df) -> "ColumnFrame":
+        import pyarrow as pa
+        return ColumnFrame.from_arrow(pa.Table.from_pandas(df, preserve_index=False))
+
+    @staticmethod
+    def from_tensors(data: dict, n_rows=None) -> "ColumnFrame":
+        """dict name -> tensor | (tensor, validity_words) | (codes, validity_words, dictionary).
+        Tensors may be torch (CUDA or CPU) or numpy; dtype float32/float64/int32/int64.
+        validity_words: int32 Arrow bitmap words (ceil(n/32)) or None."""
+        import torch
+        cols = OrderedDict()
+        for name, v in data.items():
+            dic = None
+            valid = None
+            if isinstance(v, tuple):
+                if len(v) == 3:
+                    v, valid, dic = v
+                else:
+                    v, valid = v
+            is_torch = isinstance(v, torch.Tensor)
+            npdt = np.dtype(str(v.dtype).replace("torch.", "")) if is_torch else np.asarray(v).dtype
+            if npdt not in _NP_TO_ANV:
+                raise TypeError("column %r: unsupported dtype %s" % (name, npdt))
+            anv_dt, sd = _NP_TO_ANV[npdt]
+            n = int(v.shape[0])
+            if n_rows is None:
+                n_rows = n
+            if n != n_rows:
+                raise ValueError("column %r has %d rows, expected %d" % (name, n, n_rows))
+            if dic is not None:
+                sd = "string"
+                if anv_dt != _lib.ANV_I32:
+                    raise TypeError("dictionary codes must be int32")
+            if is_torch and v.is_cuda:
+                if v.data_ptr() % 16 or not v.is_contiguous():
+                    v = v.contiguous().clone()
+                col = Column(name, sd, n, dev=v, dev_valid=valid, anv_dtype=anv_dt, dictionary=dic)
+            else:
+                hv = v.numpy() if is_torch else np.ascontiguousarray(v)
+                hvalid = None
+                if valid is not None:
+                    hvalid = valid.numpy() if isinstance(valid, torch.Tensor) else np.ascontiguousarray(valid)
+                col = Column(name, sd, n, host=hv, host_valid=hvalid, anv_dtype=anv_dt, dictionary=dic)
+            cols[name] = col
+        return ColumnFrame(cols, n_rows or 0)
+
+    # ---- device descriptors -----------------------------------------------------------
+    def descriptors(self, names):
+        """Device array of anv_column_t for `names` (kept alive by the returned tensor)."""
+        torch = _lib.require_cuda()
+        key = ("desc", tuple(names))
+        hit = self._cache.get(key)
+        if hit is not None:
+            return hit
+        arr = (_lib.AnvColumn * max(len(names), 1))()
+        keep = []
+        for i, nme in enumerate(names):
+            col = self._cols[nme]
+            d, v = col.device()
+            if d.data_ptr() % 16:
+                raise _lib.AnvError("column %r is not 16-byte aligned" % nme)
+            arr[i].data = d.data_ptr()
+            arr[i].validity = v.data_ptr() if v is not None else None
+            arr[i].dtype = col.anv_dtype
+            keep.append((d, v))
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        dev = host.cuda()
+        self._cache[key] = (dev, keep)
+        return dev, keep
+
+
+def as_frame(idf) -> ColumnFrame:
+    if isinstance(idf, ColumnFrame):
+        return idf
+    mod = type(idf).__module__
+    if mod.startswith("pyarrow"):
+        return ColumnFrame.from_arrow(idf)
+    if mod.startswith("pandas"):
+        return ColumnFrame.from_pandas(idf)
+    if isinstance(idf, dict):
+        return ColumnFrame.from_tensors(idf)
+    if hasattr(idf, "toPandas"):  # a Spark DataFrame, when pyspark is installed
+        return ColumnFrame.from_pandas(idf.toPandas())
+    raise TypeError("unsupported frame type %r: pass a ColumnFrame, pyarrow Table, pandas DataFrame or dict of tensors"
+                    % type(idf))

@@ -524,9 +524,10 @@ def _group_counts(table, col, is_binned_numeric):
             u = u.tolist()
         for k, v in zip(u, c.tolist()):
             groups[k] = int(v)
-    if (~valid).any() and is_binned_numeric:
+    has_null = bool((~valid).any())
+    if has_null and is_binned_numeric:
         groups[-1] = 0
-    return groups
+    return groups, (has_null and not is_binned_numeric)
 
 
 def statistics(idf_target, idf_source, *, list_of_cols="all", drop_cols=None, method_type="PSI",
@@ -559,25 +560,28 @@ def statistics(idf_target, idf_source, *, list_of_cols="all", drop_cols=None, me
         binned = c in num_cols
         if pre_existing_source:
             f = pd.read_csv(os.path.join(model_path, "frequency_counts", c, "part-00000.csv"))
-            src = {k: v for k, v in zip(f[c].tolist(), f["p"].tolist())}
+            src = {k: v for k, v in zip(f[c].tolist(), f["p"].tolist()) if not (isinstance(k, float) and math.isnan(k))}
+            src_null = len(src) != len(f)
             src_p_direct = True
         else:
-            src = _group_counts(source_bin, c, binned)
+            src, src_null = _group_counts(source_bin, c, binned)
             src_p_direct = False
             if source_save:
                 d = os.path.join(model_path, "frequency_counts", c)
                 os.makedirs(d, exist_ok=True)
-                keys = sorted(src, key=lambda k: (k is None, k))
-                pd.DataFrame({c: keys, "p": [src[k] / n_s for k in keys]}).to_csv(
+                keys = sorted(src)
+                kcol, pcol = ([None] if src_null else []) + keys, ([0.0] if src_null else []) + [src[k] / n_s for k in keys]
+                pd.DataFrame({c: kcol, "p": pcol}).to_csv(
                     os.path.join(d, "part-00000.csv"), index=False)
-        tgt = _group_counts(target_bin, c, binned)
+        tgt, tgt_null = _group_counts(target_bin, c, binned)
         keys = sorted(set(src) | set(tgt))
+        nulls = int(src_null) + int(tgt_null)
         if src_p_direct:
             # p comes from the saved CSV (drift_detector.py:245-250): already proportions
             tgt_p = {k: v / n_t for k, v in tgt.items()}
-            psi, hd, jsd, ks = S.drift_from_groups(src, tgt_p, 1, 1, keys)
+            psi, hd, jsd, ks = S.drift_from_groups(src, tgt_p, 1, 1, keys, nulls)
         else:
-            psi, hd, jsd, ks = S.drift_from_groups(src, tgt, n_s, n_t, keys)
+            psi, hd, jsd, ks = S.drift_from_groups(src, tgt, n_s, n_t, keys, nulls)
         if psi is None:
             psi = hd = jsd = ks = None
         row = {"attribute": c}

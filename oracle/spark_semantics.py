@@ -280,15 +280,28 @@ def assign_bins(x64: np.ndarray, valid: np.ndarray, cutoffs, bin_size: int) -> n
 # ----------------------------------------------------------------------------
 
 
-def drift_from_groups(src_groups, tgt_groups, n_src: int, n_tgt: int, ordered_keys):
+def drift_from_groups(src_groups, tgt_groups, n_src: int, n_tgt: int, ordered_keys, null_rows: int = 0):
     """src_groups / tgt_groups: dict key -> count of NON-NULL rows in the group
     (the null group is present with count 0 when the column has nulls).
     ordered_keys: every key present on either side, in `orderBy(i)` order.
+    null_rows: string columns keep their null group key as SQL NULL, which never
+    matches in the full-outer join (:266): each side's null group becomes its own row
+    (p or q = 0 -> 1e-4, other side missing -> 1e-4), sorted first (NULLS FIRST).
     Returns PSI, HD, JSD, KS (no rounding)."""
     psi = hd = pm = qm = 0.0
     cp = cq = 0.0
     ks = 0.0
-    any_row = False
+    any_row = null_rows > 0
+    for _ in range(null_rows):
+        p = q = 0.0001
+        psi += (p - q) * math.log(p / q)
+        hd += (math.sqrt(p) - math.sqrt(q)) ** 2
+        m = (p + q) / 2
+        pm += p * math.log(p / m)
+        qm += q * math.log(q / m)
+        cp += p
+        cq += q
+        ks = max(ks, abs(cp - cq))
     for k in ordered_keys:
         ps = src_groups.get(k)
         qs = tgt_groups.get(k)

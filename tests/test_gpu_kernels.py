@@ -1,0 +1,173 @@
+"""GPU parity tests of the raw kernels (through the C-ABI) against the oracle."""
+import math
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import spark_semantics as S
+
+
+def _mixed_table(n, seed=0, null_rate=0.1):
+    rng = np.random.default_rng(seed)
+    def mask():
+        return rng.random(n) < null_rate
+    cols = {
+        "f32_norm": pa.array((rng.normal(1000.0, 3.0, n)).astype(np.float32), mask=mask()),
+        "f32_logn": pa.array(np.exp(rng.normal(0, 0.75, n)).astype(np.float32)),
+        "f32_zero": pa.array(np.where(rng.random(n) < 0.7, 0.0, rng.exponential(2.0, n)).astype(np.float32), mask=mask()),
+        "f64_unif": pa.array(rng.uniform(-5, 12, n), mask=mask()),
+        "i32": pa.array(rng.integers(-50, 1000, n).astype(np.int32), mask=mask()),
+        "i64": pa.array(rng.integers(-10**12, 10**12, n).astype(np.int64)),
+        "f32_allnull": pa.array(np.zeros(n, np.float32), mask=np.ones(n, bool)),
+        "f32_const": pa.array(np.full(n, 3.25, np.float32)),
+    }
+    return pa.table(cols)
+
+
+@pytest.mark.parametrize("n", [1, 5, 33, 1000, 16384 + 7, 300001])
+def test_moments_vs_oracle(n):
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    t = _mixed_table(n, seed=n)
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    m = engine.moments(fr, names)
+    for i, c in enumerate(names):
+        vals, valid = S.column_values(t, c)
+        x = vals[valid].astype(np.float64)
+        nn, mean, m2, m3, m4 = S.central_moments(x)
+        assert m["n_valid"][i] == nn, c                                   # bit-exact counts
+        assert m["n_nonzero"][i] == int(np.count_nonzero(x != 0)), c
+        if nn == 0:
+            assert math.isnan(m["min"][i]) and math.isnan(m["max"][i])
+            continue
+        assert m["min"][i] == x.min() and m["max"][i] == x.max(), c      # bit-exact extrema
+        scale = max(abs(mean), math.sqrt(m2 / nn), 1e-300)
+        assert abs(m["mean"][i] - mean) <= 1e-9 * scale, c
+        for k, (g, e) in enumerate(((m["m2"][i], m2), (m["m3"][i], m3), (m["m4"][i], m4))):
+            tol = 1e-6 * abs(e) + 1e-9 * (m2 / nn) ** ((k + 2) / 2) * nn   # 1e-6 relative (north_star)
+            assert abs(g - e) <= tol, (c, k + 2, g, e)
+
+
+@pytest.mark.parametrize("bins", [2, 10, 20, 39, 64, 300])
+def test_histogram_bit_exact(bins):
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    n = 200003
+    t = _mixed_table(n, seed=bins).drop_columns(["f32_allnull"])
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    mom = engine.moments(fr, names)
+    cuts, lohi = [], []
+    for i, c in enumerate(names):
+        mn, mx = float(mom["min"][i]), float(mom["max"][i])
+        cuts.append(S.equal_range_cutoffs(mn, mx, bins))
+        lohi.append((mn, mx))
+    model = engine.BinModel(fr, names, cuts, lohi)
+    assert model.specs_host["mode"][names.index("f32_logn")] == 1
+    assert model.specs_host["mode"][names.index("f32_const")] == 0   # degenerate range -> generic path
+    h = engine.histogram(fr, model)
+    m2, h2 = engine.moments_histogram(fr, model)
+    assert (h == h2).all()
+    for f in engine.MOMENT_FIELDS:
+        assert np.array_equal(mom[f], m2[f], equal_nan=True), f
+    ids = engine.bin_assign(fr, model).cpu().numpy()
+    for i, c in enumerate(names):
+        vals, valid = S.column_values(t, c)
+        exp = S.assign_bins(vals.astype(np.float64), valid, cuts[i], bins)
+        if vals.dtype == np.int64:  # python compares int with float exactly; float64(v) rounds above 2^53 (not hit here)
+            pass
+        assert np.array_equal(ids[i], exp), c                              # bit-exact bin ids
+        cnt = np.bincount(exp, minlength=bins + 1)
+        assert np.array_equal(h[i, :bins + 1], cnt.astype(np.uint64)), c   # bit-exact counts
+
+
+def test_histogram_generic_cutoffs_with_duplicates():
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    n = 100000
+    t = _mixed_table(n, seed=7).select(["f32_zero", "f32_norm", "i32", "f64_unif"])
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    cuts = []
+    for c in names:
+        vals, valid = S.column_values(t, c)
+        srt = np.sort(vals[valid].astype(np.float64))
+        cuts.append(S.equal_frequency_cutoffs(srt, 10))
+    assert len(set(cuts[0])) < 9  # zero-inflated: duplicated cutoffs
+    model = engine.BinModel(fr, names, cuts, None)
+    h = engine.histogram(fr, model)
+    for i, c in enumerate(names):
+        vals, valid = S.column_values(t, c)
+        exp = S.assign_bins(vals.astype(np.float64), valid, cuts[i], 10)
+        assert np.array_equal(h[i, :11], np.bincount(exp, minlength=11).astype(np.uint64)), c
+
+
+def test_code_counts_and_drift_reduce():
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    rng = np.random.default_rng(3)
+    n = 120000
+    cats = {}
+    for card in (2, 12, 100, 12000):
+        dic = np.array(["cat_%05d" % i for i in range(card)], dtype=object)
+        codes = np.minimum((rng.pareto(1.2, n)).astype(np.int64), card - 1)
+        cats["c%d" % card] = pa.array(dic[codes], mask=rng.random(n) < 0.05)
+    t = pa.table(cats)
+    fr = ColumnFrame.from_arrow(t)
+    counts = engine.code_counts(fr, t.column_names)
+    for c, h in zip(t.column_names, counts):
+        col = fr.column(c)
+        vals, valid = S.column_values(t, c)
+        assert h[0] == int((~valid).sum())
+        u, k = np.unique(vals[valid].astype(str), return_counts=True)
+        got = {col.dictionary[i]: int(h[i + 1]) for i in range(len(col.dictionary)) if h[i + 1]}
+        assert got == dict(zip(u.tolist(), k.tolist())), c
+    # drift reduce vs the oracle's sequential loop
+    src = [np.array([5, 0, 10, 20, 0, 7], np.uint64), np.array([0, 3, 3, 0], np.uint64), np.array([2, 0, 9], np.uint64)]
+    tgt = [np.array([0, 4, 0, 25, 0, 9], np.uint64), np.array([0, 3, 3, 0], np.uint64), np.array([1, 4, 9], np.uint64)]
+    kinds = [0, 0, 1]
+    ns, nt = 42, 38
+    d = engine.drift_reduce(src, tgt, kinds, ns, nt)
+    for i in range(3):
+        sg = {k: int(v) for k, v in enumerate(src[i]) if k and v}
+        tg = {k: int(v) for k, v in enumerate(tgt[i]) if k and v}
+        nulls = 0
+        if kinds[i] == 0:
+            if src[i][0]:
+                sg[-1] = 0
+            if tgt[i][0]:
+                tg[-1] = 0
+        else:
+            nulls = int(src[i][0] > 0) + int(tgt[i][0] > 0)
+        keys = sorted(set(sg) | set(tg))
+        e = S.drift_from_groups(sg, tg, ns, nt, keys, nulls)
+        for g, ev in zip((d["psi"][i], d["hd"][i], d["jsd"][i], d["ks"][i]), e):
+            assert abs(g - ev) <= 1e-12 * max(1.0, abs(ev)), (i, g, ev)
+
+
+def test_synth_generator_reproducible_and_sane():
+    import ctypes as C
+    import torch
+    from anovos_b200 import _lib, engine
+    L = _lib.lib()
+    n = 1000003
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for rep in range(2):
+        x = torch.empty(n, dtype=torch.float32, device="cuda")
+        v = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+        _lib.check(L.anv_synth_f32(x.data_ptr(), v.data_ptr(), n, 42, 3, 0, 5.0, 2.0, 0.02, st))
+        outs.append((x.cpu().numpy(), v.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    x, v = outs[0]
+    valid = np.unpackbits(v.view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert abs(valid.mean() - 0.98) < 2e-3
+    assert abs(x.mean() - 5.0) < 0.02 and abs(x.std() - 2.0) < 0.02
+    c = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(L.anv_synth_codes(c.data_ptr(), None, n, 42, 9, 100, 1.2, 0.0, st))
+    cc = c.cpu().numpy()
+    assert cc.min() == 0 and cc.max() <= 99 and np.bincount(cc)[0] > np.bincount(cc, minlength=100)[50]
