@@ -393,10 +393,10 @@ static int pick_tile_rows(int64_t n_rows, int n_cols) {
   return (int)t;
 }
 
-static size_t hist_smem(int count_stride, int* path, int* thr_slots) {
+static size_t hist_smem(int count_stride, int* path, int* thr_slots, bool codes = false) {
   int nb = count_stride - 1, p2 = 2;
   while (p2 < nb) p2 <<= 1;
-  *thr_slots = p2 + 2;
+  *thr_slots = codes ? 2 : p2 + 2;  // dictionary codes need no thresholds
   size_t thr = (size_t)(*thr_slots) * 8;
   if (count_stride <= 40) { *path = 0; return thr + (size_t)count_stride * ANV_BLOCK * 4; }
   if (count_stride <= 10240) { *path = 1; return thr + (size_t)count_stride * 4; }
@@ -460,6 +460,7 @@ extern "C" int anv_hist(const anv_column_t* cols, const anv_binspec_t* specs, co
   if (int e = check_common(cols, n_cols, n_rows)) return e;
   if (n_cols == 0) return ANV_OK;
   if (!specs || !counts || count_stride < 2) { set_error("anv_hist: bad specs/counts/count_stride"); return ANV_ERR_INVALID; }
+  if (count_stride > 16385) { set_error("anv_hist: more than 16384 bins per column is not supported"); return ANV_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   ANV_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_cols * count_stride * sizeof(uint64_t), st));
   ScanParams P{};
@@ -487,7 +488,7 @@ extern "C" int anv_hist_codes(const anv_column_t* cols, const int32_t* cardinali
   P.card = cardinality;
   P.counts = reinterpret_cast<unsigned long long*>(counts); P.count_stride = count_stride;
   int path = 0;
-  size_t smem = hist_smem(count_stride, &path, &P.thr_slots);
+  size_t smem = hist_smem(count_stride, &path, &P.thr_slots, true);
   if (path == 0) return launch_scan<false, 0, false>(P, smem, st);
   if (path == 1) return launch_scan<false, 1, false>(P, smem, st);
   return launch_scan<false, 2, false>(P, smem, st);
@@ -499,6 +500,7 @@ extern "C" int anv_moments_hist(const anv_column_t* cols, const anv_binspec_t* s
   if (int e = check_common(cols, n_cols, n_rows)) return e;
   if (n_cols == 0) return ANV_OK;
   if (!specs || !counts || !out || count_stride < 2) { set_error("anv_moments_hist: bad arguments"); return ANV_ERR_INVALID; }
+  if (count_stride > 16385) { set_error("anv_moments_hist: more than 16384 bins per column is not supported"); return ANV_ERR_UNSUPPORTED; }
   if (workspace_bytes < anv_moments_workspace_bytes(n_cols, n_rows) || !workspace) {
     set_error("anv_moments_hist: workspace too small");
     return ANV_ERR_WORKSPACE;

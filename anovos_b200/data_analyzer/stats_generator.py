@@ -1,0 +1,330 @@
+"""B200 implementation of `anovos.data_analyzer.stats_generator` (reference
+/root/reference/src/main/anovos/data_analyzer/stats_generator.py:33-1011): same function
+names, arguments, output columns, rounding and error behaviour; `spark` is accepted and
+ignored (it may be None), `idf` is anything `anovos_b200.frame.as_frame` accepts.  All
+per-row work runs in the CUDA kernels of libanovos_b200.so; this module only normalises
+arguments and post-processes one small row per attribute on the host.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from .. import profile
+from ..frame import as_frame
+from ..result import ResultFrame
+from ..shared.utils import attributeType_segregation, jvm_double_str, spark_round
+
+_R = spark_round
+
+
+def _names(x):
+    if isinstance(x, str):
+        return [s.strip() for s in x.split("|")]
+    return list(x)
+
+
+def _unique(cols, drop):
+    # the reference does list(set(...)) - arbitrary order; we keep first-seen order (SURVEY C#7)
+    seen, out = set(), []
+    for c in cols:
+        if c not in drop and c not in seen:
+            seen.add(c)
+            out.append(c)
+    return out
+
+
+def _empty(cols):
+    return ResultFrame(pd.DataFrame({c: pd.Series([], dtype=object) for c in cols}))
+
+
+def _show(odf, n, print_impact):
+    if print_impact:
+        odf.show(max(n, 1))
+    return odf
+
+
+def _disp(col, v):
+    """summary() prints FloatType min/max/percentiles with Float.toString and Anovos casts the
+    string back to double (stats_generator.py:818-822,910-912); other dtypes are unchanged."""
+    if v is None:
+        return None
+    if col.sdtype == "float":
+        return float(str(np.float32(v)))
+    return float(v)
+
+
+def global_summary(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :33-113 - every value is a string."""
+    fr = as_frame(idf)
+    if isinstance(list_of_cols, str) and list_of_cols == "all":
+        list_of_cols = fr.columns
+    cols = _unique(_names(list_of_cols), _names(drop_cols))
+    if any(c not in fr.columns for c in cols) or not cols:
+        raise TypeError("Invalid input for Column(s)")
+    num, cat, other = attributeType_segregation(fr.select(cols))
+    if print_impact:
+        print("No. of Rows: %s" % "{0:,}".format(fr.count()))
+        print("No. of Columns: %s" % "{0:,}".format(len(cols)))
+        print("Numerical Columns: %s" % "{0:,}".format(len(num)))
+        if num:
+            print(num)
+        print("Categorical Columns: %s" % "{0:,}".format(len(cat)))
+        if cat:
+            print(cat)
+        if other:
+            print("Other Columns: %s" % "{0:,}".format(len(other)))
+            print(other)
+    rows = [["rows_count", str(fr.count())], ["columns_count", str(len(cols))],
+            ["numcols_count", str(len(num))], ["numcols_name", ", ".join(num)],
+            ["catcols_count", str(len(cat))], ["catcols_name", ", ".join(cat)],
+            ["othercols_count", str(len(other))], ["othercols_name", ", ".join(other)]]
+    return ResultFrame(pd.DataFrame(rows, columns=["metric", "value"]))
+
+
+def _discrete_cols(fr, list_of_cols, drop_cols, allow_empty=False):
+    """The "all -> num + cat" normalisation idiom (reference :150-161 and its copies)."""
+    if isinstance(list_of_cols, str) and list_of_cols == "all":
+        num, cat, _ = attributeType_segregation(fr)
+        list_of_cols = num + cat
+    cols = _unique(_names(list_of_cols), _names(drop_cols))
+    if any(c not in fr.columns for c in cols) or (not cols and not allow_empty):
+        raise TypeError("Invalid input for Column(s)")
+    bad = [c for c in cols if fr.column(c).kind == "other"]
+    if bad:
+        raise TypeError("Invalid input for Column(s): dtype of %s is not numerical/categorical" % bad)
+    return cols
+
+
+def _numeric_cols(fr, list_of_cols, drop_cols):
+    """The "all -> num" idiom of the numeric-only functions (reference :217-224, :784-795 ...)."""
+    num = attributeType_segregation(fr)[0]
+    if isinstance(list_of_cols, str) and list_of_cols == "all":
+        list_of_cols = num
+    cols = _unique(_names(list_of_cols), _names(drop_cols))
+    if any(c not in num for c in cols):
+        raise TypeError("Invalid input for Column(s)")
+    return cols
+
+
+def missingCount_computation(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :116-176: missing_count = N - count(col); missing_pct = round(missing/N, 4)."""
+    fr = as_frame(idf)
+    cols = _discrete_cols(fr, list_of_cols, drop_cols)
+    N = fr.count()
+    nv = profile.n_valid(fr, cols)
+    rows = [[c, N - nv[c], _R((N - nv[c]) / N) if N else None] for c in cols]
+    return _show(ResultFrame(pd.DataFrame(rows, columns=["attribute", "missing_count", "missing_pct"])),
+                 len(cols), print_impact)
+
+
+def nonzeroCount_computation(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :179-248 (MLlib colStats.numNonzeros after fillna(0)); pct over ALL rows."""
+    fr = as_frame(idf)
+    cols = _numeric_cols(fr, list_of_cols, drop_cols)
+    if not cols:
+        warnings.warn("No Non-Zero Count Computation - No numerical column(s) to analyze")
+        return _empty(["attribute", "nonzero_count", "nonzero_pct"])
+    N = fr.count()
+    m = profile.moments(fr, cols)
+    rows = [[c, int(m[c]["n_nonzero"]), _R(int(m[c]["n_nonzero"]) / N)] for c in cols]
+    return _show(ResultFrame(pd.DataFrame(rows, columns=["attribute", "nonzero_count", "nonzero_pct"])),
+                 len(cols), print_impact)
+
+
+def measures_of_counts(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :251-325.  missing_pct = round(1 - round(fill/N, 4), 4) (quirk kept, :313-319)."""
+    fr = as_frame(idf)
+    cols = _discrete_cols(fr, list_of_cols, drop_cols)
+    N = fr.count()
+    m = profile.moments(fr, cols)
+    rows = []
+    for c in cols:
+        fill = int(m[c]["n_valid"])
+        fill_pct = _R(fill / N)
+        row = [c, fill, fill_pct, N - fill, _R(1 - fill_pct)]
+        if fr.column(c).kind == "num":
+            nz = int(m[c]["n_nonzero"])
+            row += [nz, _R(nz / N)]
+        else:
+            row += [None, None]
+        rows.append(row)
+    odf = pd.DataFrame(rows, columns=["attribute", "fill_count", "fill_pct", "missing_count", "missing_pct",
+                                      "nonzero_count", "nonzero_pct"])
+    return _show(ResultFrame(odf), len(cols), print_impact)
+
+
+def _mode_str(col, value):
+    if value is None:
+        return None
+    if col.kind == "cat":
+        return str(value)
+    if col.sdtype in ("int", "bigint", "long"):
+        return str(int(value))
+    return jvm_double_str(float(value))
+
+
+def mode_computation(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :328-421: most frequent non-null value (as string) and its row count."""
+    fr = as_frame(idf)
+    cols = _discrete_cols(fr, list_of_cols, drop_cols, allow_empty=True)
+    if not cols:
+        warnings.warn("No Mode Computation - No discrete column(s) to analyze")
+        return _empty(["attribute", "mode", "mode_rows"])
+    md = profile.mode_distinct(fr, cols)
+    rows = [[c, _mode_str(fr.column(c), md[c][0]), md[c][1]] for c in cols if md[c][1] is not None]
+    return _show(ResultFrame(pd.DataFrame(rows, columns=["attribute", "mode", "mode_rows"])), len(cols), print_impact)
+
+
+def measures_of_centralTendency(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :424-526: mean, median (numeric only), mode, mode_rows, mode_pct."""
+    fr = as_frame(idf)
+    cols = _discrete_cols(fr, list_of_cols, drop_cols)
+    num = [c for c in cols if fr.column(c).kind == "num"]
+    m = profile.moments(fr, cols)
+    med = profile.quantiles(fr, num, [0.5])
+    md = profile.mode_distinct(fr, cols)
+    rows = []
+    for c in cols:
+        col = fr.column(c)
+        nv = int(m[c]["n_valid"])
+        mean = median = None
+        if col.kind == "num" and nv:
+            mean = _R(float(m[c]["mean"]))
+            median = _R(_disp(col, med[c][0]))
+        mode, rows_ = md[c][0], md[c][1]
+        rows.append([c, mean, median, _mode_str(col, mode), rows_, None if rows_ is None else _R(rows_ / nv)])
+    odf = pd.DataFrame(rows, columns=["attribute", "mean", "median", "mode", "mode_rows", "mode_pct"])
+    return _show(ResultFrame(odf), len(cols), print_impact)
+
+
+def _unique_values(fr, cols, approx, rsd):
+    """-> dict name -> (unique_values, hll_bias_band_flag)."""
+    out = {}
+    if approx:
+        est = profile.hll(fr, cols, rsd)
+        band = [c for c in cols if est[c][1]]
+        exact = profile.mode_distinct(fr, band) if band else {}
+        for c in cols:
+            # HLL++ bias-correction tables are unavailable offline: in that band fall back to the
+            # exact distinct count and flag the row ("parity unpinned")
+            out[c] = (exact[c][2], True) if c in exact else (est[c][0], False)
+    else:
+        md = profile.mode_distinct(fr, cols)
+        for c in cols:
+            out[c] = (md[c][2], False)
+    return out
+
+
+def uniqueCount_computation(spark, idf, list_of_cols="all", drop_cols=[], compute_approx_unique_count=False,
+                            rsd=None, print_impact=False):
+    """reference :529-620: countDistinct or approx_count_distinct(col, rsd) (HLL++)."""
+    fr = as_frame(idf)
+    cols = _discrete_cols(fr, list_of_cols, drop_cols, allow_empty=True)
+    if rsd is not None and rsd < 0:
+        raise ValueError("rsd value can not be less than 0 (default value is 0.05)")
+    if not cols:
+        warnings.warn("No Unique Count Computation - No discrete column(s) to analyze")
+        return _empty(["attribute", "unique_values"])
+    u = _unique_values(fr, cols, compute_approx_unique_count, rsd)
+    odf = pd.DataFrame([[c, int(u[c][0])] for c in cols], columns=["attribute", "unique_values"])
+    return _show(ResultFrame(odf), len(cols), print_impact)
+
+
+def measures_of_cardinality(spark, idf, list_of_cols="all", drop_cols=[], use_approx_unique_count=True, rsd=None,
+                            print_impact=False):
+    """reference :623-733: unique_values + IDness = round(unique / (N - missing), 4)."""
+    fr = as_frame(idf)
+    cols = _discrete_cols(fr, list_of_cols, drop_cols, allow_empty=True)
+    if rsd is not None and rsd < 0:
+        raise ValueError("rsd value can not be less than 0 (default value is 0.05)")
+    if not cols:
+        warnings.warn("No Cardinality Computation - No discrete column(s) to analyze")
+        return _empty(["attribute", "unique_values", "IDness"])
+    u = _unique_values(fr, cols, use_approx_unique_count, rsd)
+    nv = profile.n_valid(fr, cols)
+    rows = [[c, int(u[c][0]), _R(u[c][0] / nv[c]) if nv[c] else None] for c in cols]
+    odf = pd.DataFrame(rows, columns=["attribute", "unique_values", "IDness"])
+    odf.attrs["hll_bias_band"] = [c for c in cols if u[c][1]]
+    return _show(ResultFrame(odf), len(cols), print_impact)
+
+
+def _stddev(rec):
+    n = int(rec["n_valid"])
+    if n <= 1:
+        return None  # stddev_samp of <= 1 value: null (Spark >= 3.1 default; parity unpinned)
+    return math.sqrt(float(rec["m2"]) / (n - 1))
+
+
+def measures_of_dispersion(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :736-829.  variance = round(round(stddev,4)^2, 4); cov = round(round(stddev,4)/mean, 4)."""
+    fr = as_frame(idf)
+    cols = _numeric_cols(fr, list_of_cols, drop_cols)
+    if not cols:
+        warnings.warn("No Dispersion Computation - No numerical column(s) to analyze")
+        return _empty(["attribute", "stddev", "variance", "cov", "IQR", "range"])
+    m = profile.moments(fr, cols)
+    q = profile.quantiles(fr, cols, [0.25, 0.75])
+    rows = []
+    for c in cols:
+        col, rec = fr.column(c), m[c]
+        if int(rec["n_valid"]) == 0:
+            rows.append([c, None, None, None, None, None])
+            continue
+        sd = _R(_stddev(rec))
+        mean = float(rec["mean"])
+        var = None if sd is None else _R(sd * sd)
+        cov = None if (sd is None or mean == 0) else _R(sd / mean)   # x / 0 is null in Spark SQL
+        iqr = _R(_disp(col, q[c][1]) - _disp(col, q[c][0]))
+        rng = _R(_disp(col, float(rec["max"])) - _disp(col, float(rec["min"])))
+        rows.append([c, sd, var, cov, iqr, rng])
+    odf = pd.DataFrame(rows, columns=["attribute", "stddev", "variance", "cov", "IQR", "range"])
+    return _show(ResultFrame(odf), len(cols), print_impact)
+
+
+_PCT = [("1%", 0.01), ("5%", 0.05), ("10%", 0.1), ("25%", 0.25), ("50%", 0.5), ("75%", 0.75), ("90%", 0.9),
+        ("95%", 0.95), ("99%", 0.99)]
+
+
+def measures_of_percentiles(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :832-916: min, 1..99 %, max, each round(..., 4); percentile p = element of rank
+    ceil(p * n) (exact; Spark's GK sketch is within 1e-4 * n ranks of it)."""
+    fr = as_frame(idf)
+    cols = _numeric_cols(fr, list_of_cols, drop_cols)
+    names = ["attribute", "min"] + [p for p, _ in _PCT] + ["max"]
+    if not cols:
+        warnings.warn("No Percentiles Computation - No numerical column(s) to analyze")
+        return _empty(names)
+    m = profile.moments(fr, cols)
+    q = profile.quantiles(fr, cols, [p for _, p in _PCT])
+    rows = []
+    for c in cols:
+        col, rec = fr.column(c), m[c]
+        if int(rec["n_valid"]) == 0:
+            rows.append([c] + [None] * 11)
+            continue
+        rows.append([c, _R(_disp(col, float(rec["min"])))] + [_R(_disp(col, v)) for v in q[c]]
+                    + [_R(_disp(col, float(rec["max"])))])
+    return _show(ResultFrame(pd.DataFrame(rows, columns=names)), len(cols), print_impact)
+
+
+def measures_of_shape(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
+    """reference :919-1011: population skewness sqrt(n) M3 / M2^1.5, excess kurtosis n M4 / M2^2 - 3."""
+    fr = as_frame(idf)
+    cols = _numeric_cols(fr, list_of_cols, drop_cols)
+    if not cols:
+        warnings.warn("No Skewness/Kurtosis Computation - No numerical column(s) to analyze")
+        return _empty(["attribute", "skewness", "kurtosis"])
+    m = profile.moments(fr, cols)
+    rows = []
+    for c in cols:
+        n, m2, m3, m4 = int(m[c]["n_valid"]), float(m[c]["m2"]), float(m[c]["m3"]), float(m[c]["m4"])
+        if n == 0 or m2 == 0:
+            rows.append([c, None, None])   # Spark >= 3.1: null when M2 == 0 (parity unpinned)
+            continue
+        rows.append([c, _R(math.sqrt(n) * m3 / math.sqrt(m2 * m2 * m2)), _R(n * m4 / (m2 * m2) - 3.0)])
+    return _show(ResultFrame(pd.DataFrame(rows, columns=["attribute", "skewness", "kurtosis"])), len(cols),
+                 print_impact)

@@ -261,3 +261,150 @@ def drift_reduce(src_counts, tgt_counts, kinds, n_src, n_tgt, src_p=None):
                                   n, stride, int(n_src), int(n_tgt), out.data_ptr(), _stream()), "anv_drift_reduce")
     launch_count += 1
     return out.cpu().numpy().view(_DRIFT_DT).copy()
+
+
+# ---- K4 ---------------------------------------------------------------------------------
+
+def quantile_ranks(n_valid: int, probs):
+    """Spark rank rule: 1-based rank max(1, ceil(p * n)) with p * n in float64."""
+    return [max(1, int(math.ceil(p * n_valid))) if n_valid > 0 else 0 for p in probs]
+
+
+def select_ranks(frame: ColumnFrame, names, ranks):
+    """ranks: int64 array [n_cols, n_ranks] of 1-based ranks among non-null values (0 = skip).
+    -> float64 array [n_cols, n_ranks] of the exact order statistics (NaN where skipped)."""
+    global launch_count
+    _lib.require_cuda()
+    L = _lib.lib()
+    names = list(names)
+    ranks = np.ascontiguousarray(ranks, dtype=np.int64).reshape(len(names), -1)
+    out = np.full(ranks.shape, np.nan, np.float64)
+    if not names or ranks.shape[1] == 0:
+        return out
+    groups = {}
+    for i, nme in enumerate(names):
+        kb = 32 if frame.column(nme).anv_dtype in (_lib.ANV_F32, _lib.ANV_I32) else 64
+        groups.setdefault(kb, []).append(i)
+    for kb, idx in groups.items():
+        for r0 in range(0, ranks.shape[1], 16):
+            rk = np.ascontiguousarray(ranks[idx, r0:r0 + 16])
+            grp = [names[i] for i in idx]
+            desc, keep = frame.descriptors(grp)
+            ws_bytes = L.anv_select_workspace_bytes(len(grp), rk.shape[1])
+            ws = _dev_bytes(ws_bytes)
+            drk = _to_dev(rk)
+            dout = _dev_bytes(rk.size * 8)
+            _lib.check(L.anv_select_ranks(desc.data_ptr(), len(grp), frame.n_rows, drk.data_ptr(), rk.shape[1], kb,
+                                          dout.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "anv_select_ranks")
+            launch_count += 2 * (3 if kb == 32 else 7)
+            out[np.asarray(idx)[:, None], np.arange(r0, r0 + rk.shape[1])[None, :]] = \
+                dout.cpu().numpy().view(np.float64)[:rk.size].reshape(rk.shape)
+    return out
+
+
+# ---- sort-based exact mode / distinct --------------------------------------------------------
+
+SORT_WORKSPACE_BUDGET = 24 << 30  # bytes of scratch one sort batch may use
+
+
+def sort_mode_distinct(frame: ColumnFrame, names):
+    """-> list of (mode value | None, mode_rows | None, n_distinct) for NUMERIC columns."""
+    global launch_count
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    names = list(names)
+    res = {}
+    groups = {}
+    for nme in names:
+        kb = 32 if frame.column(nme).anv_dtype in (_lib.ANV_F32, _lib.ANV_I32) else 64
+        groups.setdefault(kb, []).append(nme)
+    for kb, grp in groups.items():
+        per_col = L.anv_mode_distinct_workspace_bytes(1, frame.n_rows, kb)
+        free = torch.cuda.mem_get_info()[0]
+        budget = min(SORT_WORKSPACE_BUDGET, int(free * 0.8))
+        batch = max(1, min(len(grp), budget // max(per_col, 1)))
+        for b0 in range(0, len(grp), batch):
+            sub = grp[b0:b0 + batch]
+            desc, keep = frame.descriptors(sub)
+            ws_bytes = L.anv_mode_distinct_workspace_bytes(len(sub), frame.n_rows, kb)
+            ws = _dev_bytes(ws_bytes)
+            n = len(sub)
+            mv, mr, nd = _dev_bytes(n * 8), _dev_bytes(n * 8), _dev_bytes(n * 8)
+            _lib.check(L.anv_mode_distinct(desc.data_ptr(), n, frame.n_rows, kb, mv.data_ptr(), mr.data_ptr(),
+                                           nd.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "anv_mode_distinct")
+            launch_count += 3 + 3 * (kb // 8)
+            hv = mv.cpu().numpy().view(np.float64)[:n]
+            hr = mr.cpu().numpy().view(np.int64)[:n]
+            hd = nd.cpu().numpy().view(np.int64)[:n]
+            del ws
+            for i, nme in enumerate(sub):
+                res[nme] = (float(hv[i]), int(hr[i]), int(hd[i])) if hr[i] > 0 else (None, None, 0)
+    return [res[n] for n in names]
+
+
+# ---- HLL++ -------------------------------------------------------------------------------------
+
+_HLL_T = {4: 10, 5: 20, 6: 40, 7: 80, 8: 220, 9: 400, 10: 900, 11: 1800, 12: 3100, 13: 6500, 14: 11500,
+          15: 20000, 16: 50000, 17: 120000, 18: 350000}
+
+
+def hll_estimate_from_registers(regs: np.ndarray, p: int):
+    """HyperLogLogPlusPlusHelper.query restated: linear counting below the threshold, raw
+    estimate above 5m; in between Spark subtracts an empirical bias (tables not available
+    offline) -> returned with band=True so the caller can fall back."""
+    m = 1 << p
+    z = float(np.sum(np.ldexp(1.0, -regs.astype(np.int64))))
+    v = int(np.count_nonzero(regs == 0))
+    alpha = {4: 0.673, 5: 0.697, 6: 0.709}.get(p, 0.7213 / (1.0 + 1.079 / m))
+    e = alpha * m * m / z
+    if v > 0:
+        h = m * math.log(m / v)
+        if h <= _HLL_T[p]:
+            return int(math.floor(h + 0.5)), False
+    if e >= 5.0 * m:
+        return int(math.floor(e + 0.5)), False
+    return int(math.floor(e + 0.5)), True
+
+
+def hll_estimates(frame: ColumnFrame, names, p: int):
+    """-> list of (estimate, in_bias_band) matching Spark's approx_count_distinct."""
+    global launch_count
+    _lib.require_cuda()
+    L = _lib.lib()
+    names = list(names)
+    m = 1 << p
+    out = {}
+    num = [n for n in names if frame.column(n).kind == "num"]
+    cat = [n for n in names if frame.column(n).kind == "cat"]
+    if num:
+        desc, keep = frame.descriptors(num)
+        regs = _dev_bytes(len(num) * m * 4)
+        _lib.check(L.anv_hll_registers(desc.data_ptr(), len(num), frame.n_rows, p, regs.data_ptr(), _stream()),
+                   "anv_hll_registers")
+        launch_count += 1
+        R = regs.cpu().numpy().view(np.uint32).reshape(len(num), m)
+        for i, n in enumerate(num):
+            out[n] = hll_estimate_from_registers(R[i], p)
+    if cat:
+        # per-row work (the code histogram) runs on the device; only the dictionary entries that
+        # actually occur are hashed on the host, once each
+        cc = code_counts(frame, cat)
+        for n, h in zip(cat, cc):
+            dic = frame.column(n).dictionary
+            present = [dic[i].encode("utf-8") for i in np.flatnonzero(h[1:])]
+            regs = np.zeros(m, np.uint32)
+            if present:
+                offs = np.zeros(len(present) + 1, np.int64)
+                np.cumsum([len(b) for b in present], out=offs[1:])
+                blob = np.frombuffer(b"".join(present) or b"\0", dtype=np.uint8)
+                hs = np.zeros(len(present), np.uint64)
+                _lib.check(L.anv_xxh64_utf8(blob.ctypes.data, offs.ctypes.data, len(present), hs.ctypes.data),
+                           "anv_xxh64_utf8")
+                idx = (hs >> np.uint64(64 - p)).astype(np.int64)
+                w = (hs << np.uint64(p)) | np.uint64(1 << (p - 1))
+                rho = np.zeros(len(hs), np.uint32)
+                for i, x in enumerate(w.tolist()):
+                    rho[i] = 64 - x.bit_length() + 1
+                np.maximum.at(regs, idx, rho)
+            out[n] = hll_estimate_from_registers(regs, p)
+    return [out[n] for n in names]

@@ -116,8 +116,8 @@ class Column:
         if self.kind == "other":
             raise _lib.AnvError("column %r has dtype %s which the hot path does not process" % (self.name, self.sdtype))
         if self._dev is None:
-            t = torch.from_numpy(self._host)
-            self._dev = t.cuda(non_blocking=False)
+            h = self._host if self._host.flags.writeable else self._host.copy()
+            self._dev = torch.from_numpy(h).cuda(non_blocking=False)
             if self._host_valid is not None:
                 self._dev_valid = torch.from_numpy(self._host_valid).cuda(non_blocking=False)
         return self._dev, self._dev_valid

@@ -1,0 +1,103 @@
+"""Per-frame cache of kernel results so that the seven stats functions (and drift) scan a
+frame once per kind of pass instead of once per function (the reference re-reads the input
+~2C+10 times for a full stats_generator block)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _lib, engine
+from .frame import ColumnFrame
+
+
+def _cache(frame: ColumnFrame, key):
+    return frame._cache.setdefault(key, {})
+
+
+def moments(frame: ColumnFrame, names):
+    """dict name -> numpy record (n_valid, n_nonzero, min, max, mean, m2, m3, m4)."""
+    c = _cache(frame, "moments")
+    todo = [n for n in names if n not in c]
+    if todo:
+        res = engine.moments(frame, todo)
+        for n, r in zip(todo, res):
+            c[n] = r
+    return {n: c[n] for n in names}
+
+
+def n_valid(frame: ColumnFrame, names):
+    """Non-null counts of numeric AND categorical columns (dictionary codes are I32 columns,
+    so the same fused pass counts them)."""
+    m = moments(frame, names)
+    return {n: int(m[n]["n_valid"]) for n in names}
+
+
+def quantiles(frame: ColumnFrame, names, probs):
+    """dict name -> list of exact order statistics at rank max(1, ceil(p*n)) (None if empty)."""
+    c = _cache(frame, "quantiles")
+    mom = moments(frame, names)
+    want = {}
+    for n in names:
+        nv = int(mom[n]["n_valid"])
+        want[n] = engine.quantile_ranks(nv, probs)
+    todo = [n for n in names if any(r and (n, r) not in c for r in want[n])]
+    if todo:
+        width = max(len([r for r in want[n] if r]) for n in todo)
+        rk = np.zeros((len(todo), max(width, 1)), np.int64)
+        for i, n in enumerate(todo):
+            rs = sorted(set(r for r in want[n] if r))
+            rk[i, :len(rs)] = rs
+        vals = engine.select_ranks(frame, todo, rk)
+        for i, n in enumerate(todo):
+            for r, v in zip(rk[i], vals[i]):
+                if r:
+                    c[(n, int(r))] = float(v)
+    return {n: [c[(n, r)] if r else None for r in want[n]] for n in names}
+
+
+def code_counts(frame: ColumnFrame, names):
+    """dict name -> uint64 counts [cardinality + 1], slot 0 = nulls (string columns)."""
+    c = _cache(frame, "codes")
+    todo = [n for n in names if n not in c]
+    if todo:
+        for n, h in zip(todo, engine.code_counts(frame, todo)):
+            c[n] = h
+    return {n: c[n] for n in names}
+
+
+def mode_distinct(frame: ColumnFrame, names):
+    """dict name -> (mode value | None, mode_rows | None, n_distinct) over non-null values.
+    Ties: smallest value (numeric) / smallest UTF-8 string (categorical); the reference's
+    choice is arbitrary (stats_generator.py:358)."""
+    c = _cache(frame, "mode")
+    todo = [n for n in names if n not in c]
+    cat = [n for n in todo if frame.column(n).kind == "cat"]
+    num = [n for n in todo if frame.column(n).kind == "num"]
+    if cat:
+        cc = code_counts(frame, cat)
+        for n in cat:
+            h = cc[n][1:]
+            dic = frame.column(n).dictionary
+            if len(dic) == 0 or h.sum() == 0:
+                c[n] = (None, None, 0)
+                continue
+            mx = int(h.max())
+            best = min((dic[i] for i in np.flatnonzero(h == mx)), key=lambda s: s.encode("utf-8"))
+            c[n] = (best, mx, int(np.count_nonzero(h)))
+    if num:
+        for n, r in zip(num, engine.sort_mode_distinct(frame, num)):
+            c[n] = r
+    return {n: c[n] for n in names}
+
+
+def hll(frame: ColumnFrame, names, rsd):
+    """dict name -> (estimate, in_bias_band) of Spark's approx_count_distinct(col, rsd)."""
+    rsd = 0.05 if rsd is None else rsd
+    p = int(math.ceil(2.0 * math.log(1.106 / rsd) / math.log(2.0)))
+    c = _cache(frame, ("hll", p))
+    todo = [n for n in names if n not in c]
+    if todo:
+        for n, r in zip(todo, engine.hll_estimates(frame, todo, p)):
+            c[n] = r
+    return {n: c[n] for n in names}

@@ -1,0 +1,70 @@
+"""Host helpers mirroring reference shared/utils.py (attributeType_segregation :48-73,
+get_dtype :76-90, ends_with :93-110) plus the Spark formatting rules the result frames
+need (round HALF_UP, Double.toString)."""
+from __future__ import annotations
+
+import math
+from decimal import ROUND_HALF_UP, Decimal
+
+from ..frame import as_frame, kind_of
+
+_QUANT = {4: Decimal("0.0001")}
+
+
+def attributeType_segregation(idf):
+    """-> (num_cols, cat_cols, other_cols) by Spark dtype string (shared/utils.py:64-72)."""
+    fr = as_frame(idf)
+    out = {"num": [], "cat": [], "other": []}
+    for name, sd in fr.dtypes:
+        out[kind_of(sd)].append(name)
+    return out["num"], out["cat"], out["other"]
+
+
+def get_dtype(idf, col):
+    return [d for n, d in as_frame(idf).dtypes if n == col][0]
+
+
+def ends_with(string, end_str="/"):
+    string = str(string)
+    return string if string.endswith(end_str) else string + end_str
+
+
+def spark_round(x, scale=4):
+    """F.round(double, scale): HALF_UP on the shortest decimal repr of the double."""
+    if x is None:
+        return None
+    x = float(x)
+    if x != x or x in (math.inf, -math.inf):
+        return x
+    q = _QUANT.get(scale)
+    if q is None:
+        q = _QUANT[scale] = Decimal(1).scaleb(-scale)
+    return float(Decimal(repr(x)).quantize(q, rounding=ROUND_HALF_UP))
+
+
+def jvm_double_str(x: float) -> str:
+    """java.lang.Double.toString of x: decimal notation for 1e-3 <= |x| < 1e7, otherwise
+    d.dddE[-]n (what `mode` looks like after the reference casts it to string,
+    stats_generator.py:405-411)."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (math.inf, -math.inf):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == 0:
+        return "-0.0" if math.copysign(1.0, x) < 0 else "0.0"
+    sign, digits, exp = Decimal(repr(x)).as_tuple()
+    ds = "".join(map(str, digits)).rstrip("0") or "0"
+    exp += len(digits) - len(ds) if ds != "0" else 0
+    # value = 0.ds * 10**point
+    point = len(ds) + exp
+    neg = "-" if sign else ""
+    if 1e-3 <= abs(x) < 1e7:
+        if point <= 0:
+            body = "0." + "0" * (-point) + ds
+        elif point >= len(ds):
+            body = ds + "0" * (point - len(ds)) + ".0"
+        else:
+            body = ds[:point] + "." + ds[point:]
+        return neg + body
+    return "%s%s.%sE%d" % (neg, ds[0], ds[1:] or "0", point - 1)

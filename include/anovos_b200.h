@@ -135,6 +135,38 @@ int anv_drift_reduce(const uint64_t* src_counts, const uint64_t* tgt_counts, con
                      int src_is_p, const int32_t* n_slots, const int32_t* kind, int n_cols,
                      int count_stride, int64_t n_src, int64_t n_tgt, anv_drift_t* out, void* stream);
 
+/* ---- K4: exact multi-rank selection (Spark summary() percentiles / approxQuantile,
+ *      stats_generator.py:488,813,908; transformers.py:215) by radix select on the
+ *      order-preserving integer image of the values (NaN sorts last, -0.0 == 0.0).
+ * ranks [dev] n_cols * n_ranks 1-based ranks among the NON-NULL values (0 = skip,
+ * n_ranks <= 16); out [dev] n_cols * n_ranks doubles (NaN when skipped).
+ * key_bits: 32 when every column is F32/I32 (3 passes), else 64 (7 passes). */
+size_t anv_select_workspace_bytes(int n_cols, int n_ranks);
+int anv_select_ranks(const anv_column_t* cols, int n_cols, int64_t n_rows, const int64_t* ranks,
+                     int n_ranks, int key_bits, double* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---- K6: HyperLogLog++ registers of approx_count_distinct(col, rsd) (stats_generator.py:
+ *      605-608): Spark's XXH64 (seed 42) per-type encoding - I32 hashInt, I64 hashLong,
+ *      F32 hashInt(floatToIntBits), F64 hashLong(doubleToLongBits), -0.0 -> 0.0 - then
+ *      idx = top p bits, rho = clz(rest)+1, register = max.  regs [dev] (n_cols << p) uint32. */
+int anv_hll_registers(const anv_column_t* cols, int n_cols, int64_t n_rows, int p, uint32_t* regs,
+                      void* stream);
+/* Host helper: the same XXH64 over n UTF-8 strings (Arrow offsets) for the dictionaries of
+ * string columns.  bytes/offsets/out are HOST pointers. */
+int anv_xxh64_utf8(const uint8_t* bytes, const int64_t* offsets, int64_t n, uint64_t* out);
+
+/* ---- exact mode / distinct count of numeric columns (mode_computation's per-column
+ *      groupBy+sort jobs, stats_generator.py:386-401; countDistinct, :611): batched LSD
+ *      radix sort of the non-null values' order-preserving keys + run-length summary.
+ * key_bits 32 (all columns F32/I32) or 64.  Outputs [dev] n_cols each: mode_value (NaN when
+ * the column has no non-null value; ties -> smallest value), mode_rows, n_distinct
+ * (-0.0 == 0.0, all NaNs equal). */
+size_t anv_mode_distinct_workspace_bytes(int n_cols, int64_t n_rows, int key_bits);
+int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, int key_bits,
+                      double* mode_value, int64_t* mode_rows, int64_t* n_distinct, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* ---- synthetic column generator used by bench.py / tests: Philox4x32-10
  *      keyed by (seed, column), counter = row.  family: 0 normal(a,b) 1 lognormal(0,b)
  *      2 uniform(a,b) 3 zero-inflated exponential(scale b, 70% zeros).

@@ -171,3 +171,71 @@ def test_synth_generator_reproducible_and_sane():
     _lib.check(L.anv_synth_codes(c.data_ptr(), None, n, 42, 9, 100, 1.2, 0.0, st))
     cc = c.cpu().numpy()
     assert cc.min() == 0 and cc.max() <= 99 and np.bincount(cc)[0] > np.bincount(cc, minlength=100)[50]
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 250007])
+def test_select_ranks_exact(n):
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    t = _mixed_table(n, seed=100 + n)
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    probs = [0.01, 0.05, 0.1, 0.25, 0.5, 0.75, 0.9, 0.95, 0.99, 3 * (1 / 10), 1.0]
+    ranks, exp = [], []
+    for c in names:
+        vals, valid = S.column_values(t, c)
+        srt = np.sort(vals[valid].astype(np.float64))
+        rk = engine.quantile_ranks(len(srt), probs)
+        ranks.append(rk)
+        exp.append([srt[r - 1] if r else np.nan for r in rk])
+    got = engine.select_ranks(fr, names, np.array(ranks))
+    assert np.array_equal(got, np.array(exp), equal_nan=True)   # exact order statistics
+
+
+@pytest.mark.parametrize("n", [1, 40, 5000, 200001])
+def test_mode_distinct_exact(n):
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    rng = np.random.default_rng(n)
+    t = _mixed_table(n, seed=200 + n)
+    t = t.append_column("i32_small", pa.array(rng.integers(0, 7, n).astype(np.int32), mask=rng.random(n) < 0.2))
+    t = t.append_column("f32_signed", pa.array(np.round(rng.normal(0, 3, n)).astype(np.float32)))
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    got = engine.sort_mode_distinct(fr, names)
+    for c, (mode, rows, nd) in zip(names, got):
+        vals, valid = S.column_values(t, c)
+        x = vals[valid]
+        if x.size == 0:
+            assert (mode, rows, nd) == (None, None, 0)
+            continue
+        if x.dtype.kind == "f":
+            x = x + 0.0
+        u, k = np.unique(x, return_counts=True)
+        assert nd == u.size, c                          # exact distinct
+        assert rows == int(k.max()), c                  # exact mode_rows
+        assert mode == float(u[np.argmax(k)]), c        # smallest value among ties
+
+
+def test_hll_matches_oracle_registers(income):
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    fr = ColumnFrame.from_arrow(income)
+    names = [c for c in income.column_names]
+    for p in (9, 12):
+        est = engine.hll_estimates(fr, names, p)
+        for c, (e, band) in zip(names, est):
+            vals, valid = S.column_values(income, c)
+            sd = S.spark_dtype(income.schema.field(c).type)
+            regs = S.hll_registers(S.hll_hashes(vals[valid], sd), p)
+            assert (e, band) == S.hll_estimate(regs, p), (c, p)
+    rng = np.random.default_rng(5)
+    n = 300000
+    t = pa.table({"f32": pa.array(rng.normal(0, 1, n).astype(np.float32), mask=rng.random(n) < 0.1),
+                  "f64": pa.array(np.round(rng.normal(0, 100, n), 1)),
+                  "i64": pa.array(rng.integers(-10**9, 10**9, n).astype(np.int64))})
+    fr = ColumnFrame.from_arrow(t)
+    for c, (e, band) in zip(t.column_names, engine.hll_estimates(fr, t.column_names, 14)):
+        vals, valid = S.column_values(t, c)
+        regs = S.hll_registers(S.hll_hashes(vals[valid], S.spark_dtype(t.schema.field(c).type)), 14)
+        assert (e, band) == S.hll_estimate(regs, 14), c
