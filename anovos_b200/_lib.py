@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libanovos_b200.so")
+LIB_PATH = os.environ.get("ANOVOS_B200_LIB") or os.path.join(HERE, "libanovos_b200.so")
 
 ANV_F32, ANV_F64, ANV_I32, ANV_I64 = 0, 1, 2, 3
 

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libanovos_b200.so")
-SOURCES = ["capi.cu", "scan.cu", "drift.cu", "synth.cu", "select.cu", "hll.cu", "sort.cu"]
+SOURCES = ["capi.cu", "scan_host.cu", "scan_mom.cu", "scan_hist.cu", "scan_fused.cu", "scan_assign.cu", "drift.cu", "synth.cu", "select.cu", "hll.cu", "sort.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "--expt-extended-lambda", "-Xcompiler", "-fPIC,-O3",
               "-Xptxas", "-v"]
@@ -28,6 +28,24 @@ def _stale(target, deps):
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(tag, defines):
+    """Experimental build with extra -D flags -> anovos_b200/build/variants/libanovos_b200_<tag>.so"""
+    vdir = os.path.join(HERE, "build", "variants", tag)
+    os.makedirs(vdir, exist_ok=True)
+    objs, procs = [], []
+    for s in SOURCES:
+        obj = os.path.join(vdir, s.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-D" + d for d in defines] + \
+              ["-c", os.path.join(CSRC, s), "-o", obj]
+        procs.append(subprocess.Popen(cmd))
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("nvcc failed for variant " + tag)
+    lib = os.path.join(HERE, "build", "variants", "libanovos_b200_%s.so" % tag)
+    subprocess.check_call([_nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
 
 
 def build(force=False, verbose=False):

@@ -30,6 +30,7 @@ template <> struct Traits<float> {
   using Vec = float4;
   __device__ static float lowest() { return -INFINITY; }
   __device__ static float highest() { return INFINITY; }
+  __device__ static float first_slot() { return __int_as_float(0x7fc00000); }
   __device__ static double to_double(float v) { return (double)v; }
   __device__ static bool is_nan(float v) { return v != v; }
 };
@@ -38,12 +39,14 @@ template <> struct Traits<double> {
   using Vec = double2;
   __device__ static double lowest() { return -INFINITY; }
   __device__ static double highest() { return INFINITY; }
+  __device__ static double first_slot() { return __longlong_as_double(0x7ff8000000000000ll); }
   __device__ static double to_double(double v) { return v; }
   __device__ static bool is_nan(double v) { return v != v; }
 };
 template <> struct Traits<int32_t> {
   static constexpr int VEC = 4;
   using Vec = int4;
+  __device__ static int32_t first_slot() { return INT_MIN; }
   __device__ static int32_t lowest() { return INT_MIN; }
   __device__ static int32_t highest() { return INT_MAX; }
   __device__ static double to_double(int32_t v) { return (double)v; }
@@ -52,6 +55,7 @@ template <> struct Traits<int32_t> {
 template <> struct Traits<int64_t> {
   static constexpr int VEC = 2;
   using Vec = longlong2;
+  __device__ static int64_t first_slot() { return LLONG_MIN; }
   __device__ static int64_t lowest() { return LLONG_MIN; }
   __device__ static int64_t highest() { return LLONG_MAX; }
   __device__ static double to_double(int64_t v) { return (double)v; }

@@ -24,6 +24,48 @@ _SPEC_DT = np.dtype([("n_bins", "<i4"), ("mode", "<i4"), ("lo", "<f8"), ("inv_w"
 launch_count = 0  # kernels launched through this module (bench.py reports it)
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of every C-ABI call (on the launching stream), per entry point."""
+
+    def __init__(self):
+        self.spans = []
+
+    def totals(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.spans:
+            t = out.setdefault(name, [0.0, 0])
+            t[0] += e0.elapsed_time(e1)
+            t[1] += 1
+        return {k: {"ms": v[0], "calls": v[1]} for k, v in out.items()}
+
+
+timer = None  # set to a KernelTimer() to collect per-call device times
+d2h_bytes = 0  # bytes read back from the device by this module
+
+
+def _host(t, nbytes=None):
+    """device uint8 tensor -> numpy (counts the D2H bytes)."""
+    global d2h_bytes
+    a = t.cpu().numpy()
+    d2h_bytes += a.nbytes if nbytes is None else nbytes
+    return a
+
+
+def _call(fn, name, *args):
+    if timer is None:
+        _lib.check(fn(*args), name)
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    timer.spans.append((name, e0, e1))
+    _lib.check(rc, name)
+
+
 def _stream():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -53,10 +95,10 @@ def moments(frame: ColumnFrame, names):
     ws_bytes = L.anv_moments_workspace_bytes(len(names), frame.n_rows)
     ws = _dev_bytes(ws_bytes)
     out = _dev_bytes(len(names) * _MOM_DT.itemsize)
-    _lib.check(L.anv_moments(desc.data_ptr(), len(names), frame.n_rows, out.data_ptr(), ws.data_ptr(), ws_bytes,
-                             _stream()), "anv_moments")
+    _call(L.anv_moments, "anv_moments", desc.data_ptr(), len(names), frame.n_rows, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                             _stream())
     launch_count += 2
-    return out.cpu().numpy().view(_MOM_DT).copy()
+    return _host(out).view(_MOM_DT).copy()
 
 
 # ---- binning model -> device specs ---------------------------------------------------------
@@ -152,10 +194,10 @@ def histogram(frame: ColumnFrame, model: BinModel):
     desc, keep = frame.descriptors(model.names)
     specs, cuts = model.device()
     counts = _dev_bytes(n * stride * 8)
-    _lib.check(L.anv_hist(desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, counts.data_ptr(),
-                          stride, _stream()), "anv_hist")
+    _call(L.anv_hist, "anv_hist", desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, counts.data_ptr(),
+                          stride, _stream())
     launch_count += 1
-    return counts.cpu().numpy().view(np.uint64).reshape(n, stride).copy()
+    return _host(counts).view(np.uint64).reshape(n, stride).copy()
 
 
 def moments_histogram(frame: ColumnFrame, model: BinModel):
@@ -173,11 +215,11 @@ def moments_histogram(frame: ColumnFrame, model: BinModel):
     ws_bytes = L.anv_moments_workspace_bytes(n, frame.n_rows)
     ws = _dev_bytes(ws_bytes)
     out = _dev_bytes(n * _MOM_DT.itemsize)
-    _lib.check(L.anv_moments_hist(desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, out.data_ptr(),
-                                  counts.data_ptr(), stride, ws.data_ptr(), ws_bytes, _stream()), "anv_moments_hist")
+    _call(L.anv_moments_hist, "anv_moments_hist", desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, out.data_ptr(),
+                                  counts.data_ptr(), stride, ws.data_ptr(), ws_bytes, _stream())
     launch_count += 2
-    return (out.cpu().numpy().view(_MOM_DT).copy(),
-            counts.cpu().numpy().view(np.uint64).reshape(n, stride).copy())
+    return (_host(out).view(_MOM_DT).copy(),
+            _host(counts).view(np.uint64).reshape(n, stride).copy())
 
 
 def bin_assign(frame: ColumnFrame, model: BinModel):
@@ -192,8 +234,8 @@ def bin_assign(frame: ColumnFrame, model: BinModel):
         return out[:n, :frame.n_rows]
     desc, keep = frame.descriptors(model.names)
     specs, cuts = model.device()
-    _lib.check(L.anv_bin_assign(desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, model.max_bins,
-                                out.data_ptr(), out.stride(0), _stream()), "anv_bin_assign")
+    _call(L.anv_bin_assign, "anv_bin_assign", desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, model.max_bins,
+                                out.data_ptr(), out.stride(0), _stream())
     launch_count += 1
     return out[:, :frame.n_rows]
 
@@ -217,10 +259,10 @@ def code_counts(frame: ColumnFrame, names):
         desc, keep = frame.descriptors(grp)
         dcards = _to_dev(cards)
         counts = _dev_bytes(len(grp) * stride * 8)
-        _lib.check(L.anv_hist_codes(desc.data_ptr(), dcards.data_ptr(), len(grp), frame.n_rows, counts.data_ptr(),
-                                    stride, _stream()), "anv_hist_codes")
+        _call(L.anv_hist_codes, "anv_hist_codes", desc.data_ptr(), dcards.data_ptr(), len(grp), frame.n_rows, counts.data_ptr(),
+                                    stride, _stream())
         launch_count += 1
-        h = counts.cpu().numpy().view(np.uint64).reshape(len(grp), stride)
+        h = _host(counts).view(np.uint64).reshape(len(grp), stride)
         for i, g in enumerate(grp):
             out[g] = h[i, :cards[i] + 1].copy()
     return [out[n] for n in names]
@@ -256,11 +298,11 @@ def drift_reduce(src_counts, tgt_counts, kinds, n_src, n_tgt, src_p=None):
         dS, dP, is_p = None, _to_dev(Pm), 1
     dslots, dkind = _to_dev(n_slots), _to_dev(np.asarray(kinds, dtype=np.int32))
     out = _dev_bytes(n * _DRIFT_DT.itemsize)
-    _lib.check(L.anv_drift_reduce(dS.data_ptr() if dS is not None else None, dT.data_ptr(),
+    _call(L.anv_drift_reduce, "anv_drift_reduce", dS.data_ptr() if dS is not None else None, dT.data_ptr(),
                                   dP.data_ptr() if dP is not None else None, is_p, dslots.data_ptr(), dkind.data_ptr(),
-                                  n, stride, int(n_src), int(n_tgt), out.data_ptr(), _stream()), "anv_drift_reduce")
+                                  n, stride, int(n_src), int(n_tgt), out.data_ptr(), _stream())
     launch_count += 1
-    return out.cpu().numpy().view(_DRIFT_DT).copy()
+    return _host(out).view(_DRIFT_DT).copy()
 
 
 # ---- K4 ---------------------------------------------------------------------------------
@@ -294,11 +336,11 @@ def select_ranks(frame: ColumnFrame, names, ranks):
             ws = _dev_bytes(ws_bytes)
             drk = _to_dev(rk)
             dout = _dev_bytes(rk.size * 8)
-            _lib.check(L.anv_select_ranks(desc.data_ptr(), len(grp), frame.n_rows, drk.data_ptr(), rk.shape[1], kb,
-                                          dout.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "anv_select_ranks")
+            _call(L.anv_select_ranks, "anv_select_ranks", desc.data_ptr(), len(grp), frame.n_rows, drk.data_ptr(), rk.shape[1], kb,
+                                          dout.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
             launch_count += 2 * (3 if kb == 32 else 7)
             out[np.asarray(idx)[:, None], np.arange(r0, r0 + rk.shape[1])[None, :]] = \
-                dout.cpu().numpy().view(np.float64)[:rk.size].reshape(rk.shape)
+                _host(dout).view(np.float64)[:rk.size].reshape(rk.shape)
     return out
 
 
@@ -330,12 +372,12 @@ def sort_mode_distinct(frame: ColumnFrame, names):
             ws = _dev_bytes(ws_bytes)
             n = len(sub)
             mv, mr, nd = _dev_bytes(n * 8), _dev_bytes(n * 8), _dev_bytes(n * 8)
-            _lib.check(L.anv_mode_distinct(desc.data_ptr(), n, frame.n_rows, kb, mv.data_ptr(), mr.data_ptr(),
-                                           nd.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "anv_mode_distinct")
+            _call(L.anv_mode_distinct, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv.data_ptr(), mr.data_ptr(),
+                                           nd.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
             launch_count += 3 + 3 * (kb // 8)
-            hv = mv.cpu().numpy().view(np.float64)[:n]
-            hr = mr.cpu().numpy().view(np.int64)[:n]
-            hd = nd.cpu().numpy().view(np.int64)[:n]
+            hv = _host(mv).view(np.float64)[:n]
+            hr = _host(mr).view(np.int64)[:n]
+            hd = _host(nd).view(np.int64)[:n]
             del ws
             for i, nme in enumerate(sub):
                 res[nme] = (float(hv[i]), int(hr[i]), int(hd[i])) if hr[i] > 0 else (None, None, 0)
@@ -379,10 +421,9 @@ def hll_estimates(frame: ColumnFrame, names, p: int):
     if num:
         desc, keep = frame.descriptors(num)
         regs = _dev_bytes(len(num) * m * 4)
-        _lib.check(L.anv_hll_registers(desc.data_ptr(), len(num), frame.n_rows, p, regs.data_ptr(), _stream()),
-                   "anv_hll_registers")
+        _call(L.anv_hll_registers, "anv_hll_registers", desc.data_ptr(), len(num), frame.n_rows, p, regs.data_ptr(), _stream())
         launch_count += 1
-        R = regs.cpu().numpy().view(np.uint32).reshape(len(num), m)
+        R = _host(regs).view(np.uint32).reshape(len(num), m)
         for i, n in enumerate(num):
             out[n] = hll_estimate_from_registers(R[i], p)
     if cat:
@@ -398,8 +439,7 @@ def hll_estimates(frame: ColumnFrame, names, p: int):
                 np.cumsum([len(b) for b in present], out=offs[1:])
                 blob = np.frombuffer(b"".join(present) or b"\0", dtype=np.uint8)
                 hs = np.zeros(len(present), np.uint64)
-                _lib.check(L.anv_xxh64_utf8(blob.ctypes.data, offs.ctypes.data, len(present), hs.ctypes.data),
-                           "anv_xxh64_utf8")
+                _call(L.anv_xxh64_utf8, "anv_xxh64_utf8", blob.ctypes.data, offs.ctypes.data, len(present), hs.ctypes.data)
                 idx = (hs >> np.uint64(64 - p)).astype(np.int64)
                 w = (hs << np.uint64(p)) | np.uint64(1 << (p - 1))
                 rho = np.zeros(len(hs), np.uint32)

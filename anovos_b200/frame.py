@@ -20,6 +20,8 @@ from . import _lib
 
 _NUMERIC_SPARK = ("double", "int", "bigint", "float", "long")
 
+h2d_bytes = 0  # bytes uploaded to the device by Column.device()
+
 
 def spark_dtype_of_arrow(t) -> str:
     """Arrow type -> Spark SQL dtype string as `idf.dtypes` would print it."""
@@ -116,10 +118,16 @@ class Column:
         if self.kind == "other":
             raise _lib.AnvError("column %r has dtype %s which the hot path does not process" % (self.name, self.sdtype))
         if self._dev is None:
+            global h2d_bytes
             h = self._host if self._host.flags.writeable else self._host.copy()
-            self._dev = torch.from_numpy(h).cuda(non_blocking=False)
+            t = torch.from_numpy(h)
+            # pinned host buffers upload asynchronously on the current stream (stream-ordered with the kernels)
+            self._dev = t.cuda(non_blocking=t.is_pinned())
+            h2d_bytes += h.nbytes
             if self._host_valid is not None:
-                self._dev_valid = torch.from_numpy(self._host_valid).cuda(non_blocking=False)
+                tv = torch.from_numpy(self._host_valid)
+                self._dev_valid = tv.cuda(non_blocking=tv.is_pinned())
+                h2d_bytes += self._host_valid.nbytes
         return self._dev, self._dev_valid
 
     def drop_device(self):

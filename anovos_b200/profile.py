@@ -11,6 +11,9 @@ from . import _lib, engine
 from .frame import ColumnFrame
 
 
+SUMMARY_PROBS = [0.01, 0.05, 0.1, 0.25, 0.5, 0.75, 0.9, 0.95, 0.99]
+
+
 def _cache(frame: ColumnFrame, key):
     return frame._cache.setdefault(key, {})
 
@@ -37,16 +40,20 @@ def quantiles(frame: ColumnFrame, names, probs):
     """dict name -> list of exact order statistics at rank max(1, ceil(p*n)) (None if empty)."""
     c = _cache(frame, "quantiles")
     mom = moments(frame, names)
-    want = {}
+    want, extra = {}, {}
     for n in names:
         nv = int(mom[n]["n_valid"])
         want[n] = engine.quantile_ranks(nv, probs)
+        # a select pass costs the same for 1 or 16 ranks: always resolve the nine summary()
+        # percentiles too, so median / IQR / percentiles share ONE radix select per column
+        extra[n] = engine.quantile_ranks(nv, SUMMARY_PROBS)
     todo = [n for n in names if any(r and (n, r) not in c for r in want[n])]
     if todo:
-        width = max(len([r for r in want[n] if r]) for n in todo)
+        sets = {n: sorted(set(r for r in want[n] + extra[n] if r and (n, r) not in c)) for n in todo}
+        width = max(len(v) for v in sets.values())
         rk = np.zeros((len(todo), max(width, 1)), np.int64)
         for i, n in enumerate(todo):
-            rs = sorted(set(r for r in want[n] if r))
+            rs = sets[n]
             rk[i, :len(rs)] = rs
         vals = engine.select_ranks(frame, todo, rk)
         for i, n in enumerate(todo):

@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py - the measurement contract of this repo.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: the FULL
+stats_generator (measures_of_counts / centralTendency / cardinality / dispersion /
+percentiles / shape) of a synthetic float32 frame that is already resident in HBM
+(BASELINE.json configs[1]: 10M rows x 50 cols; `--workload c3`: 100M x 200).  Rank 0
+prints ONE JSON line.  `value` = rows x cols / s over all ranks (weak scaling: every rank
+owns `cols` columns - columns shard with no data-path collective, one NCCL all_gather of
+the per-column summaries per step).  `e2e` = the same step through the public API from
+pinned HOST buffers (H2D inside the timed region).  `roofline` describes the fused
+streaming scan kernel (K1) timed with CUDA events inside the timed region.
+`--impl reference` times the CPU oracle restatement on the host cores (Spark is not
+available on the box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(rows=10_000_000, cols=50, desc="synthetic 10M rows x 50 float32 cols: full stats_generator"),
+    "c3": dict(rows=100_000_000, cols=200, desc="synthetic 100M rows x 200 float32 cols: full stats_generator"),
+    "tiny": dict(rows=200_000, cols=8, desc="smoke-size synthetic frame"),
+}
+METRIC = "rows x cols / s, full stats_generator (+ HBM GB/s of the fused scan kernel)"
+CPU_SAMPLE_ROWS = 1_000_000
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, "/tmp/anv_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the step
+# ---------------------------------------------------------------------------------------------
+
+def stats_step(frame):
+    """Full stats_generator through the public API; returns the result frames (pandas)."""
+    import anovos.data_analyzer.stats_generator as sg
+    frame._cache = {k: v for k, v in frame._cache.items() if isinstance(k, tuple) and k and k[0] == "desc"}
+    out = [sg.measures_of_counts(None, frame), sg.measures_of_centralTendency(None, frame),
+           sg.measures_of_cardinality(None, frame), sg.measures_of_dispersion(None, frame),
+           sg.measures_of_percentiles(None, frame), sg.measures_of_shape(None, frame)]
+    return [o.toPandas() for o in out]
+
+
+def summary_tensor(frames, torch):
+    """Fixed-size per-column summary (float64) exchanged between ranks: SURVEY 8(e)."""
+    import numpy as np
+    import pandas as pd
+    cols = []
+    for df in frames:
+        num = df.drop(columns=[c for c in df.columns if c in ("attribute", "mode")])
+        cols.append(num.apply(pd.to_numeric, errors="coerce").to_numpy(dtype=np.float64))
+    return torch.from_numpy(np.ascontiguousarray(np.concatenate(cols, axis=1))).cuda()
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from anovos_b200 import engine, frame as framemod, synth
+    from anovos_b200.frame import ColumnFrame
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = WORKLOADS[args.workload]
+    rows, cols = args.rows or wl["rows"], args.cols or wl["cols"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident input: this rank's column shard (weak scaling: `cols` columns per GPU) -------
+    src = synth.device_frame(rows, cols, seed=42, first_col=rank * cols)
+    torch.cuda.synchronize()
+
+    def step():
+        frames = stats_step(src)
+        if world > 1:  # the only exchange of the path: per-column summaries (tiny, latency-bound)
+            mine = summary_tensor(frames, torch)
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+        return frames
+
+    if not args.no_extras:
+        args.warmup = max(args.warmup, 3)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    engine.timer = engine.KernelTimer()
+    l0 = engine.launch_count
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = engine.launch_count - l0
+    kt = engine.timer.totals()
+    engine.timer = None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = rows * cols * world / (ms_per_step / 1e3)
+
+    # ---- roofline of the fused streaming scan kernel (K1), from the timed region -----------------
+    n_nullable = sum(1 for c in src.columns if src.column(c).has_validity)
+    alg_bytes = rows * cols * 4 + n_nullable * ((rows + 7) // 8)
+    k1 = kt.get("anv_moments", {"ms": 0.0, "calls": 0})
+    peak, peak_src = peaks()
+    k1_ms = k1["ms"] / max(k1["calls"], 1)
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    roofline = {"kernel": "scan_kernel<MOM> (anv_moments: count/nonzero/min/max/mean/M2/M3/M4, FP64)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k1_ms,
+                "share_of_step": k1["ms"] / ms if ms > 0 else None}
+    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
+                   "share_of_step": v["ms"] / ms} for k, v in sorted(kt.items())}
+
+    line = None
+    if rank == 0:
+        # ---- fused stats+histogram pass of a drift target (north-star kernel), timed alone ----------
+        extra, e2e, cpu = {}, None, None
+        if not args.no_extras:
+            try:
+                extra = fused_pass_numbers(src, rows, cols, alg_bytes, peak, torch, engine)
+            except Exception as ex:  # never lose the main line
+                extra = {"error": repr(ex)}
+            # ---- e2e: same step from pinned HOST buffers through the public API ---------------------
+            e2e = e2e_numbers(args, rows, cols, rank, torch, framemod, engine, src)
+            cpu = cpu_baseline(cols, with_drift=False)
+        line = {"metric": METRIC, "value": value, "unit": "rows*cols/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (on-device Philox: normal/lognormal/uniform/zero-inflated, null rates 0/0.1%/2%/30%)",
+                "config": {"workload": args.workload + ": " + wl["desc"], "rows": rows, "cols_per_gpu": cols,
+                           "l2": "inputs (%.1f GB per GPU) are larger than L2" % (rows * cols * 4 / 1e9),
+                           "sharding": "columns per rank, one NCCL all_gather of per-column summaries per step"},
+                "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                "kernels": kernels, "fused_stats_hist_pass": extra}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def fused_pass_numbers(src, rows, cols, alg_bytes, peak, torch, engine):
+    """anv_moments_hist (the drift target pass: moments + 10-bin histogram in one read)."""
+    import numpy as np
+    names = src.columns
+    mom = engine.moments(src, names)
+    cuts, lohi = [], []
+    for i in range(len(names)):
+        mn, mx = float(mom["min"][i]), float(mom["max"][i])
+        w = (mx - mn) / 10
+        cuts.append([mn + j * w for j in range(1, 10)])
+        lohi.append((mn, mx))
+    model = engine.BinModel(src, names, cuts, lohi)
+    out = {}
+    for name, fn in (("hist", lambda: engine.histogram(src, model)), ("fused", lambda: engine.moments_histogram(src, model))):
+        for _ in range(3):
+            fn()
+        engine.timer = engine.KernelTimer()
+        for _ in range(5):
+            fn()
+        tot = engine.timer.totals()
+        engine.timer = None
+        key = "anv_hist" if name == "hist" else "anv_moments_hist"
+        ms = tot[key]["ms"] / tot[key]["calls"]
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms_per_launch": ms, "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
+                     "rows_cols_per_s": rows * cols / (ms * 1e-3)}
+    return out
+
+
+def e2e_numbers(args, rows, cols, rank, torch, framemod, engine, src):
+    """Full step from pinned host buffers: H2D of every column + the result read-back inside
+    the timed region, through ColumnFrame.from_tensors + the stats_generator API."""
+    host = {}
+    for name in src.columns:
+        c = src.column(name)
+        d, v = c.device()
+        hd = torch.empty(d.shape, dtype=d.dtype, pin_memory=True)
+        hd.copy_(d)
+        hv = None
+        if v is not None:
+            hv = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            hv.copy_(v)
+        host[name] = (hd, hv) if hv is not None else hd
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 5))
+
+    def one():
+        fr = framemod.ColumnFrame.from_tensors(host, n_rows=rows)
+        return stats_step(fr)
+
+    one()
+    torch.cuda.synchronize()
+    h0, d0 = framemod.h2d_bytes, engine.d2h_bytes
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": rows * cols / dt, "unit": "rows*cols/s", "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": (framemod.h2d_bytes - h0) // steps, "d2h_bytes_per_step": (engine.d2h_bytes - d0) // steps,
+            "steps": steps, "note": "pinned host columns -> H2D -> 6 measures_of_* -> pandas, wall clock incl. host post-processing"}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle restatement on the host cores)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_baseline(cols, with_drift=False, rows=CPU_SAMPLE_ROWS, workers=None):
+    from anovos_b200 import synth
+    from oracle import cpu_bench
+    workers = workers or min(cols, os.cpu_count() or 1)
+    table = synth.host_table(rows, cols)
+    target = synth.host_table(rows, cols, seed=43, shifted=True) if with_drift else None
+    t_stats, t_drift, used = cpu_bench.time_stats_generator(table, workers, target)
+    out = {"value": rows * cols / t_stats, "unit": "rows*cols/s", "cores": used, "kind": "port",
+           "sample": "%d rows x %d cols of the same generator families, oracle (NumPy restatement of the Spark "
+                     "semantics, not Spark), one process per column, %.2f s" % (rows, cols, t_stats),
+           "host_cores": os.cpu_count()}
+    if t_drift is not None:
+        out["drift_value"] = rows * cols / t_drift
+    return out
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path.  Spark/JVM are not installed on the box, so
+    this is the oracle port on all host cores, on bounded samples of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    cols = args.cols or wl["cols"]
+    rows = min(args.rows or wl["rows"], CPU_SAMPLE_ROWS)
+    from anovos_b200 import synth
+    from oracle import cpu_bench
+    workers = min(cols, os.cpu_count() or 1)
+    table = synth.host_table(rows, cols)
+    times = []
+    for i in range(max(args.warmup, 1) + args.steps):
+        t, _, used = cpu_bench.time_stats_generator(table, workers)
+        if i >= max(args.warmup, 1):
+            times.append(t)
+    dt = sum(times) / len(times)
+    v = rows * cols / dt
+    cpu = {"value": v, "unit": "rows*cols/s", "cores": used, "kind": "port",
+           "sample": "%d rows x %d cols per step (bounded sample of %s)" % (rows, cols, args.workload)}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "rows*cols/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic (NumPy twin of the device generator)",
+                      "config": {"workload": args.workload + ": " + wl["desc"], "rows": rows, "cols_per_gpu": cols},
+                      "cpu_baseline": cpu,
+                      "e2e": {"value": v, "unit": "rows*cols/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+          flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--cols", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="profiling runs: skip e2e / cpu_baseline / fused extras")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

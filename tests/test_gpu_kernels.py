@@ -239,3 +239,38 @@ def test_hll_matches_oracle_registers(income):
         vals, valid = S.column_values(t, c)
         regs = S.hll_registers(S.hll_hashes(vals[valid], S.spark_dtype(t.schema.field(c).type)), 14)
         assert (e, band) == S.hll_estimate(regs, 14), c
+
+
+def test_moments_hist_without_early_pivot():
+    """Tiles whose first 1024+ rows are null / non-finite: the pivot fallback (null lanes
+    impersonate 0) must not pollute min / max / nonzero counts / histograms."""
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    n = 70001
+    rng = np.random.default_rng(11)
+    a = (rng.normal(7.0, 1.0, n)).astype(np.float32)          # all values > 0: a stray 0 would show in min
+    ma = np.zeros(n, bool); ma[:5000] = True; ma[rng.random(n) < 0.2] = True
+    b = np.full(n, np.inf, np.float32); mb = rng.random(n) < 0.5   # only +inf values and nulls
+    c = (-np.abs(rng.normal(3.0, 1.0, n))).astype(np.float32)  # all negative: a stray 0 would show in max
+    mc = np.zeros(n, bool); mc[:40000] = True
+    d = rng.integers(5, 50, n).astype(np.int32); md = np.zeros(n, bool); md[:3000] = True
+    t = pa.table({"a": pa.array(a, mask=ma), "b": pa.array(b, mask=mb), "c": pa.array(c, mask=mc), "d": pa.array(d, mask=md)})
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    m = engine.moments(fr, names)
+    for i, nme in enumerate(names):
+        vals, valid = S.column_values(t, nme)
+        x = vals[valid].astype(np.float64)
+        assert m["n_valid"][i] == x.size and m["n_nonzero"][i] == np.count_nonzero(x != 0), nme
+        assert m["min"][i] == x.min() and m["max"][i] == x.max(), nme
+    cuts = [S.equal_range_cutoffs(float(m["min"][i]), float(m["max"][i]), 10) if np.isfinite(m["min"][i] - m["max"][i])
+            else [1.0 * j for j in range(1, 10)] for i in range(len(names))]
+    model = engine.BinModel(fr, names, cuts, [(float(m["min"][i]), float(m["max"][i])) for i in range(len(names))])
+    h = engine.histogram(fr, model)
+    m2, h2 = engine.moments_histogram(fr, model)
+    assert (h == h2).all()
+    for i, nme in enumerate(names):
+        vals, valid = S.column_values(t, nme)
+        exp = S.assign_bins(vals.astype(np.float64), valid, cuts[i], 10)
+        assert np.array_equal(h[i, :11], np.bincount(exp, minlength=11).astype(np.uint64)), nme
+        assert m2["min"][i] == m["min"][i] and m2["max"][i] == m["max"][i] and m2["n_nonzero"][i] == m["n_nonzero"][i]
