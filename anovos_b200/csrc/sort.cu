@@ -22,7 +22,6 @@
 namespace anv {
 
 constexpr int SORT_TILE = 4096;  // keys per CTA (8 warps x 16 rounds x 32 lanes)
-constexpr int SORT_ROUNDS = SORT_TILE / ANV_BLOCK;
 
 template <typename K, typename T> __device__ __forceinline__ K make_key(T x);
 template <> __device__ __forceinline__ uint32_t make_key<uint32_t, float>(float x) {
@@ -84,38 +83,92 @@ template <typename K> struct SortParams {
   int pass;
 };
 
-// ---- pack: values -> keys, nulls dropped ------------------------------------------------------
+// ---- pack: values -> keys, nulls dropped --------------------------------------------------
+// One CTA per 4096-row tile: 128-bit loads, block-level compaction (one atomicAdd per CTA
+// reserves the output range; the order before a sort is irrelevant), 64-byte runs per thread.
 template <typename K, typename T>
-__device__ __forceinline__ void pack_column(const SortParams<K>& P, const anv_column_t& col, int c) {
-  const T* __restrict__ data = reinterpret_cast<const T*>(col.data);
+__device__ __forceinline__ void pack_tile(const SortParams<K>& P, const anv_column_t& col, int c, uint32_t* s_warp,
+                                          unsigned long long* s_base, K* sk) {
+  constexpr int VEC = Traits<T>::VEC;
+  constexpr int PER = SORT_TILE / ANV_BLOCK;  // 16 rows per thread, contiguous
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * SORT_TILE;
+  const int n_tile = (int)min((int64_t)SORT_TILE, P.n_rows - r0);
+  const T* __restrict__ data = reinterpret_cast<const T*>(col.data) + r0;
   const uint32_t* __restrict__ vbits = col.validity;
-  K* __restrict__ out = P.buf[0] + (size_t)c * P.stride;
-  unsigned long long* counter = &P.state[c].n_valid;
-  const int lane = threadIdx.x & 31;
-  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
-       base < P.n_rows; base += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = base + lane;
-    bool ok = i < P.n_rows;
-    T x = ok ? data[i] : (T)0;
-    if (ok && vbits) ok = (__ldg(vbits + (i >> 5)) >> (i & 31)) & 1u;
-    const uint32_t m = __ballot_sync(ANV_FULL, ok);
-    if (!m) continue;
-    unsigned long long pos = 0;
-    if (lane == 0) pos = atomicAdd(counter, (unsigned long long)__popc(m));
-    pos = __shfl_sync(ANV_FULL, pos, 0);
-    if (ok) out[pos + __popc(m & ((1u << lane) - 1u))] = make_key<K, T>(x);
+  const int row0 = tid * PER;
+  K keys[PER];
+  uint32_t okmask = 0;
+  if (row0 + PER <= n_tile) {
+    uint32_t vb = 0xFFFFu;
+    if (vbits) {
+      const int64_t g = r0 + row0;  // multiple of 16
+      vb = (__ldg(vbits + (g >> 5)) >> (g & 31)) & 0xFFFFu;
+    }
+    okmask = vb;
+    const uint4* p = reinterpret_cast<const uint4*>(data + row0);
+#pragma unroll
+    for (int v = 0; v < PER / VEC; ++v) {
+      const uint4 q = ldg_stream(p + v);
+      T e[VEC];
+      unpack<T>(q, e);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) keys[v * VEC + i] = make_key<K, T>(e[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int row = row0 + i;
+      bool ok = row < n_tile;
+      keys[i] = 0;
+      if (ok) {
+        if (vbits) { const int64_t g = r0 + row; ok = (vbits[g >> 5] >> (g & 31)) & 1u; }
+        keys[i] = make_key<K, T>(data[row]);
+      }
+      okmask |= ok ? (1u << i) : 0u;
+    }
   }
+  // block exclusive scan of the per-thread valid counts
+  const uint32_t mine = __popc(okmask);
+  uint32_t inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t acc = 0;
+    for (int w = 0; w < ANV_WARPS; ++w) { const uint32_t t = s_warp[w]; s_warp[w] = acc; acc += t; }
+    *s_base = acc ? atomicAdd(&P.state[c].n_valid, (unsigned long long)acc) : 0ull;
+  }
+  __syncthreads();
+  // stage the compacted keys in shared memory, then write them out coalesced
+  uint32_t o = s_warp[warp] + (inc - mine);
+#pragma unroll
+  for (int i = 0; i < PER; ++i)
+    if ((okmask >> i) & 1u) sk[o++] = keys[i];
+  __shared__ uint32_t s_total;
+  if (tid == ANV_BLOCK - 1) s_total = s_warp[warp] + inc;
+  __syncthreads();
+  K* __restrict__ out = P.buf[0] + (size_t)c * P.stride + *s_base;
+  const uint32_t total = s_total;
+  for (uint32_t i = tid; i < total; i += ANV_BLOCK) out[i] = sk[i];
 }
 
 template <typename K>
 __global__ void __launch_bounds__(ANV_BLOCK) pack_kernel(const SortParams<K> P) {
+  __shared__ uint32_t s_warp[ANV_WARPS];
+  __shared__ unsigned long long s_base;
+  __shared__ K sk[SORT_TILE];
   const int c = blockIdx.y;
   const anv_column_t col = P.cols[c];
   switch (col.dtype) {
-    case ANV_F32: pack_column<K, float>(P, col, c); break;
-    case ANV_I32: pack_column<K, int32_t>(P, col, c); break;
-    case ANV_F64: if (sizeof(K) == 8) pack_column<K, double>(P, col, c); break;
-    case ANV_I64: if (sizeof(K) == 8) pack_column<K, int64_t>(P, col, c); break;
+    case ANV_F32: pack_tile<K, float>(P, col, c, s_warp, &s_base, sk); break;
+    case ANV_I32: pack_tile<K, int32_t>(P, col, c, s_warp, &s_base, sk); break;
+    case ANV_F64: if (sizeof(K) == 8) pack_tile<K, double>(P, col, c, s_warp, &s_base, sk); break;
+    case ANV_I64: if (sizeof(K) == 8) pack_tile<K, int64_t>(P, col, c, s_warp, &s_base, sk); break;
     default: break;
   }
 }
@@ -125,9 +178,11 @@ template <typename K> __device__ __forceinline__ uint32_t digit_of(K k, int pass
 }
 
 // ---- pass step 1: per-tile digit histogram ------------------------------------------------------
+// Plain shared-memory atomics (hardware handles same-address lanes far faster than a
+// match_any pre-aggregation: measured 4-5x on B200).
 template <typename K>
 __global__ void __launch_bounds__(ANV_BLOCK) sort_hist_kernel(const SortParams<K> P) {
-  const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   const ColState& S = P.state[c];
   const int64_t n = (int64_t)S.n_valid;
   const int64_t t0 = (int64_t)tile * SORT_TILE;
@@ -135,18 +190,23 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_hist_kernel(const SortParams<K
   h[tid] = 0;
   __syncthreads();
   if (t0 < n) {
-    const K* __restrict__ keys = P.buf[S.cur] + (size_t)c * P.stride;
-#pragma unroll 4
-    for (int r = 0; r < SORT_ROUNDS; ++r) {
-      const int64_t i = t0 + r * ANV_BLOCK + tid;
-      const bool ok = i < n;
-      const uint32_t act = __ballot_sync(ANV_FULL, ok);
-      if (ok) {
-        const uint32_t d = digit_of(keys[i], P.pass);
-        const uint32_t m = __match_any_sync(act, d);
-        if (lane == __ffs(m) - 1) atomicAdd(&h[d], (uint32_t)__popc(m));
+    const K* __restrict__ keys = P.buf[S.cur] + (size_t)c * P.stride + t0;
+    const int nt = (int)min((int64_t)SORT_TILE, n - t0);
+    constexpr int KV = 16 / sizeof(K);  // keys per 128-bit load
+    const int nvec = nt / KV;
+    const uint4* __restrict__ kv = reinterpret_cast<const uint4*>(keys);
+    const int sh = P.pass * 8;
+    for (int j = tid; j < nvec; j += ANV_BLOCK) {
+      const uint4 q = kv[j];
+      if (sizeof(K) == 4) {
+        atomicAdd(&h[(q.x >> sh) & 0xFFu], 1u); atomicAdd(&h[(q.y >> sh) & 0xFFu], 1u);
+        atomicAdd(&h[(q.z >> sh) & 0xFFu], 1u); atomicAdd(&h[(q.w >> sh) & 0xFFu], 1u);
+      } else {
+        const uint64_t k0 = ((uint64_t)q.y << 32) | q.x, k1 = ((uint64_t)q.w << 32) | q.z;
+        atomicAdd(&h[(uint32_t)(k0 >> sh) & 0xFFu], 1u); atomicAdd(&h[(uint32_t)(k1 >> sh) & 0xFFu], 1u);
       }
     }
+    for (int i = nvec * KV + tid; i < nt; i += ANV_BLOCK) atomicAdd(&h[digit_of(keys[i], P.pass)], 1u);
   }
   __syncthreads();
   const uint32_t v = h[tid];
@@ -211,6 +271,11 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortParams<K> P) 
 }
 
 // ---- pass step 3: stable scatter ---------------------------------------------------------------
+// Ranking: warp w owns 512 consecutive keys (16 rounds of 32); the lanes holding the same digit
+// are found with 8 ballots (cheaper than MATCH.ANY on sm_100a), all 16 rounds' loads and peer
+// masks are computed up front (independent), then the warp-private digit counters are advanced
+// round by round.  The tile is then REORDERED IN SHARED MEMORY into digit order, so the global
+// writes are coalesced runs (full 32-byte sectors) instead of 4-byte scatters.
 template <typename K>
 __global__ void __launch_bounds__(ANV_BLOCK) sort_scatter_kernel(const SortParams<K> P) {
   const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -219,51 +284,89 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_scatter_kernel(const SortParam
   const int64_t n = (int64_t)S.n_valid;
   const int64_t t0 = (int64_t)tile * SORT_TILE;
   if (t0 >= n) return;
+  const int nt = (int)min((int64_t)SORT_TILE, n - t0);
   const int src = S.src[P.pass];
-  const K* __restrict__ in = P.buf[src] + (size_t)c * P.stride;
+  const K* __restrict__ in = P.buf[src] + (size_t)c * P.stride + t0;
   K* __restrict__ out = P.buf[src ^ 1] + (size_t)c * P.stride;
   __shared__ uint32_t wcnt[ANV_WARPS][256];
   __shared__ uint32_t gbase[256];
+  __shared__ uint32_t dstart[256];
+  __shared__ uint32_t wtot[ANV_WARPS];
+  __shared__ K sk[SORT_TILE];
   for (int i = tid; i < ANV_WARPS * 256; i += ANV_BLOCK) (&wcnt[0][0])[i] = 0;
   gbase[tid] = P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile];
-  __syncthreads();
-  // warp w owns the contiguous segment [t0 + w*512, +512): rounds of 32 consecutive keys
   constexpr int WR = SORT_TILE / ANV_WARPS / 32;  // 16 rounds per warp
   K key[WR];
-  uint32_t pos[WR];
-  const int64_t w0 = t0 + (int64_t)warp * (SORT_TILE / ANV_WARPS);
+  uint32_t peers[WR];
+  const int w0 = warp * (SORT_TILE / ANV_WARPS);
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
-    const int64_t i = w0 + r * 32 + lane;
-    const bool ok = i < n;
+    const int i = w0 + r * 32 + lane;
+    key[r] = (i < nt) ? in[i] : (K)0;
+  }
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < WR; ++r) {
+    const bool ok = (w0 + r * 32 + lane) < nt;
     const uint32_t act = __ballot_sync(ANV_FULL, ok);
-    pos[r] = 0;
-    key[r] = 0;
-    if (ok) {
-      key[r] = in[i];
-      const uint32_t d = digit_of(key[r], P.pass);
-      const uint32_t m = __match_any_sync(act, d);
-      const uint32_t before = wcnt[warp][d];
-      pos[r] = before + __popc(m & ((1u << lane) - 1u));
-      __syncwarp(m);
-      if (lane == __ffs(m) - 1) wcnt[warp][d] = before + __popc(m);
+    const uint32_t d = digit_of(key[r], P.pass);
+    uint32_t m = act;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const uint32_t bal = __ballot_sync(ANV_FULL, bit);
+      m &= bit ? bal : ~bal;
     }
+    peers[r] = ok ? m : 0u;
+  }
+  __syncthreads();
+  uint32_t pos[WR];
+#pragma unroll
+  for (int r = 0; r < WR; ++r) {
+    const uint32_t m = peers[r];
+    const uint32_t d = digit_of(key[r], P.pass);
+    uint32_t before = 0;
+    if (m) before = wcnt[warp][d];
+    pos[r] = before + __popc(m & lt);
+    __syncwarp();
+    if (m && lane == __ffs(m) - 1) wcnt[warp][d] = before + __popc(m);
     __syncwarp();
   }
   __syncthreads();
-  {  // exclusive prefix over warps for digit `tid`
+  uint32_t total;
+  {  // exclusive prefix over warps for digit `tid`, tile total of the digit
     uint32_t acc = 0;
 #pragma unroll
     for (int w = 0; w < ANV_WARPS; ++w) { const uint32_t t = wcnt[w][tid]; wcnt[w][tid] = acc; acc += t; }
+    total = acc;
+  }
+  {  // exclusive scan of the 256 digit totals -> start of each digit inside the reordered tile
+    uint32_t inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < ANV_WARPS; ++w) woff += (w < warp) ? wtot[w] : 0u;
+    dstart[tid] = woff + inc - total;
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
-    const int64_t i = w0 + r * 32 + lane;
-    if (i < n) {
+    if (peers[r]) {
       const uint32_t d = digit_of(key[r], P.pass);
-      out[(size_t)gbase[d] + wcnt[warp][d] + pos[r]] = key[r];
+      sk[dstart[d] + wcnt[warp][d] + pos[r]] = key[r];
     }
+  }
+  __syncthreads();
+  for (int p = tid; p < nt; p += ANV_BLOCK) {
+    const K k = sk[p];
+    const uint32_t d = digit_of(k, P.pass);
+    out[(size_t)gbase[d] + (p - dstart[d])] = k;
   }
 }
 
@@ -318,45 +421,96 @@ __global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K>
   }
 }
 
+// Associative combine of two ADJACENT run summaries (left, right) of sorted keys.
+template <typename K> __device__ __forceinline__ void best_of(K& bk, uint32_t& bl, K k, uint32_t len) {
+  if (len > bl) { bl = len; bk = k; }  // candidates arrive in ascending key order: strict > keeps the smallest key
+}
 template <typename K>
-__global__ void run_merge_kernel(const SortParams<K> P, double* mode_value, int64_t* mode_rows, int64_t* n_distinct) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.n_cols) return;
+__device__ __forceinline__ TileSummary<K> combine(const TileSummary<K>& L, const TileSummary<K>& R) {
+  if (L.n == 0) return R;
+  if (R.n == 0) return L;
+  TileSummary<K> o;
+  const bool same = L.last_key == R.first_key;
+  const bool Ls = L.prefix_len == L.n, Rs = R.prefix_len == R.n;  // the whole side is one run
+  o.first_key = L.first_key; o.last_key = R.last_key; o.n = L.n + R.n;
+  o.heads_inside = L.heads_inside + R.heads_inside + (same ? 0u : 1u);
+  o.prefix_len = (Ls && same) ? L.n + R.prefix_len : L.prefix_len;
+  o.suffix_len = (Rs && same) ? R.n + L.suffix_len : R.suffix_len;
+  K bk = 0; uint32_t bl = 0;
+  if (L.best_len) best_of(bk, bl, L.best_key, L.best_len);
+  if (same) {
+    if (!Ls && !Rs) best_of(bk, bl, L.last_key, L.suffix_len + R.prefix_len);
+  } else {
+    if (!Ls) best_of(bk, bl, L.last_key, L.suffix_len);
+    if (!Rs) best_of(bk, bl, R.first_key, R.prefix_len);
+  }
+  if (R.best_len) best_of(bk, bl, R.best_key, R.best_len);
+  o.best_key = bk; o.best_len = bl;
+  return o;
+}
+template <typename K> __device__ __forceinline__ K shfl_down_key(K v, int d) {
+  if (sizeof(K) == 8) return (K)__shfl_down_sync(ANV_FULL, (unsigned long long)v, d);
+  return (K)__shfl_down_sync(ANV_FULL, (uint32_t)v, d);
+}
+template <typename K> __device__ __forceinline__ TileSummary<K> shfl_down_summary(const TileSummary<K>& s, int d) {
+  TileSummary<K> r;
+  r.first_key = shfl_down_key(s.first_key, d); r.last_key = shfl_down_key(s.last_key, d);
+  r.best_key = shfl_down_key(s.best_key, d);
+  r.n = __shfl_down_sync(ANV_FULL, s.n, d); r.prefix_len = __shfl_down_sync(ANV_FULL, s.prefix_len, d);
+  r.suffix_len = __shfl_down_sync(ANV_FULL, s.suffix_len, d); r.best_len = __shfl_down_sync(ANV_FULL, s.best_len, d);
+  r.heads_inside = __shfl_down_sync(ANV_FULL, s.heads_inside, d);
+  return r;
+}
+
+// One warp per column: 32 tile summaries per step are combined with an order-preserving
+// shuffle tree, the chunk results sequentially by lane 0.  Also reads the requested order
+// statistics straight out of the sorted keys.
+template <typename K>
+__global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, double* mode_value, int64_t* mode_rows,
+                                                       int64_t* n_distinct, const int64_t* ranks, int n_ranks,
+                                                       double* rank_values) {
+  const int c = blockIdx.x, lane = threadIdx.x;
   const ColState& S = P.state[c];
   const int64_t n = (int64_t)S.n_valid;
   const int dt = P.cols[c].dtype;
-  if (n == 0) { mode_value[c] = nan(""); mode_rows[c] = 0; n_distinct[c] = 0; return; }
+  const K* __restrict__ sorted = P.buf[S.cur] + (size_t)c * P.stride;
+  for (int r = lane; r < n_ranks; r += 32) {
+    const int64_t rk = ranks[(size_t)c * n_ranks + r];
+    double v = nan("");
+    if (rk > 0 && rk <= n) {
+      const K k = sorted[rk - 1];
+      v = sorted_key_to_double(sizeof(K) == 8 ? (uint64_t)k : ((uint64_t)k << 32), dt);
+    }
+    rank_values[(size_t)c * n_ranks + r] = v;
+  }
+  if (n == 0) {
+    if (lane == 0) { mode_value[c] = nan(""); mode_rows[c] = 0; n_distinct[c] = 0; }
+    return;
+  }
   const TileSummary<K>* T = P.summ + (size_t)c * P.n_tiles;
   const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
-  K best_key = 0, carry_key = 0, prev_last = 0;
-  int64_t best_len = 0, carry_len = 0, distinct = 0;
-  auto close = [&](K k, int64_t len) {  // runs are closed in ascending key order: strict > keeps the smallest key
-    if (len > best_len) { best_len = len; best_key = k; }
-  };
-  for (int t = 0; t < tiles; ++t) {
-    const TileSummary<K> s = T[t];
-    distinct += s.heads_inside + ((t == 0 || s.first_key != prev_last) ? 1 : 0);
-    const bool single = s.prefix_len == s.n;
-    if (carry_len && carry_key == s.first_key) {
-      carry_len += s.prefix_len;
-    } else {
-      if (carry_len) close(carry_key, carry_len);
-      carry_key = s.first_key;
-      carry_len = s.prefix_len;
+  TileSummary<K> acc;
+  acc.n = 0;
+  for (int t0 = 0; t0 < tiles; t0 += 32) {
+    TileSummary<K> mine;
+    mine.n = 0;
+    if (t0 + lane < tiles) mine = T[t0 + lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const TileSummary<K> right = shfl_down_summary(mine, o);
+      if ((lane & (2 * o - 1)) == 0) mine = combine(mine, right);
     }
-    if (!single) {
-      close(carry_key, carry_len);
-      if (s.best_len) close(s.best_key, s.best_len);
-      carry_key = s.last_key;
-      carry_len = s.suffix_len;
-    }
-    prev_last = s.last_key;
+    if (lane == 0) acc = combine(acc, mine);
   }
-  if (carry_len) close(carry_key, carry_len);
-  const uint64_t k64 = sizeof(K) == 8 ? (uint64_t)best_key : ((uint64_t)best_key << 32);
-  mode_value[c] = sorted_key_to_double(k64, dt);
-  mode_rows[c] = best_len;
-  n_distinct[c] = distinct;
+  if (lane == 0) {
+    K bk = 0; uint32_t bl = 0;
+    best_of(bk, bl, acc.first_key, acc.prefix_len);
+    if (acc.best_len) best_of(bk, bl, acc.best_key, acc.best_len);
+    if (acc.prefix_len != acc.n) best_of(bk, bl, acc.last_key, acc.suffix_len);
+    mode_value[c] = sorted_key_to_double(sizeof(K) == 8 ? (uint64_t)bk : ((uint64_t)bk << 32), dt);
+    mode_rows[c] = bl;
+    n_distinct[c] = (int64_t)acc.heads_inside + 1;
+  }
 }
 
 template <typename K> struct Layout {
@@ -378,7 +532,8 @@ template <typename K> struct Layout {
 
 template <typename K>
 static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, double* mode_value, int64_t* mode_rows,
-                             int64_t* n_distinct, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                             int64_t* n_distinct, const int64_t* ranks, int n_ranks, double* rank_values, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st) {
   Layout<K> L(n_cols, n_rows);
   if (workspace_bytes < L.total) { set_error("anv_mode_distinct: workspace too small (%zu < %zu)", workspace_bytes, L.total); return ANV_ERR_WORKSPACE; }
   char* w = reinterpret_cast<char*>(workspace);
@@ -396,11 +551,9 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   ANV_CUDA(cudaMemsetAsync(P.state, 0, (size_t)n_cols * sizeof(ColState), st));
   ANV_CUDA(cudaMemsetAsync(P.digit_total, 0, (size_t)n_cols * 256 * 8, st));
   if (n_rows > 0) {
-    int pack_blocks = (int)((n_rows + ANV_BLOCK * 8 - 1) / (ANV_BLOCK * 8));
-    if (pack_blocks > 148 * 8) pack_blocks = 148 * 8;
-    pack_kernel<K><<<dim3(pack_blocks, n_cols), ANV_BLOCK, 0, st>>>(P);
-    ANV_CUDA(cudaGetLastError());
     dim3 grid(P.n_tiles, n_cols);
+    pack_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
+    ANV_CUDA(cudaGetLastError());
     for (int pass = 0; pass < (int)sizeof(K); ++pass) {
       P.pass = pass;
       sort_hist_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
@@ -411,7 +564,7 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
     run_tile_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
     ANV_CUDA(cudaGetLastError());
   }
-  run_merge_kernel<K><<<(n_cols + 31) / 32, 32, 0, st>>>(P, mode_value, mode_rows, n_distinct);
+  run_merge_kernel<K><<<n_cols, 32, 0, st>>>(P, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values);
   ANV_CUDA(cudaGetLastError());
   return ANV_OK;
 }
@@ -426,14 +579,15 @@ extern "C" size_t anv_mode_distinct_workspace_bytes(int n_cols, int64_t n_rows, 
 }
 
 extern "C" int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, int key_bits, double* mode_value,
-                                 int64_t* mode_rows, int64_t* n_distinct, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+                                 int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks, int n_ranks,
+                                 double* rank_values, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_ranks < 0 || (n_ranks > 0 && (!ranks || !rank_values))) { set_error("anv_mode_distinct: bad ranks arguments"); return ANV_ERR_INVALID; }
   if (n_cols < 0 || n_rows < 0 || (key_bits != 32 && key_bits != 64)) { set_error("anv_mode_distinct: bad arguments"); return ANV_ERR_INVALID; }
   if (n_cols == 0) return ANV_OK;
   if (n_cols > 65535) { set_error("n_cols > 65535"); return ANV_ERR_UNSUPPORTED; }
   if (n_rows >= ((int64_t)1 << 32)) { set_error("anv_mode_distinct: n_rows >= 2^32 per call is not supported"); return ANV_ERR_UNSUPPORTED; }
   if (!cols || !mode_value || !mode_rows || !n_distinct || !workspace) { set_error("anv_mode_distinct: NULL argument"); return ANV_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (key_bits == 32) return run_mode_distinct<uint32_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, workspace, workspace_bytes, st);
-  return run_mode_distinct<uint64_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, workspace, workspace_bytes, st);
+  if (key_bits == 32) return run_mode_distinct<uint32_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, workspace, workspace_bytes, st);
+  return run_mode_distinct<uint64_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, workspace, workspace_bytes, st);
 }

@@ -185,8 +185,8 @@ def measures_of_centralTendency(spark, idf, list_of_cols="all", drop_cols=[], pr
     cols = _discrete_cols(fr, list_of_cols, drop_cols)
     num = [c for c in cols if fr.column(c).kind == "num"]
     m = profile.moments(fr, cols)
+    md = profile.mode_distinct(fr, cols)       # the sort also yields the exact percentiles (cached)
     med = profile.quantiles(fr, num, [0.5])
-    md = profile.mode_distinct(fr, cols)
     rows = []
     for c in cols:
         col = fr.column(c)

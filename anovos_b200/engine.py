@@ -349,39 +349,54 @@ def select_ranks(frame: ColumnFrame, names, ranks):
 SORT_WORKSPACE_BUDGET = 24 << 30  # bytes of scratch one sort batch may use
 
 
-def sort_mode_distinct(frame: ColumnFrame, names):
-    """-> list of (mode value | None, mode_rows | None, n_distinct) for NUMERIC columns."""
+def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
+    """-> list of (mode value | None, mode_rows | None, n_distinct) for NUMERIC columns.
+    ranks: optional int64 [n_cols, n_ranks] of 1-based ranks among the non-null values (0 = skip);
+    then returns (list, float64 [n_cols, n_ranks]) with the exact order statistics read from the
+    sorted keys."""
     global launch_count
     torch = _lib.require_cuda()
     L = _lib.lib()
     names = list(names)
+    n_ranks = 0
+    if ranks is not None:
+        ranks = np.ascontiguousarray(ranks, dtype=np.int64).reshape(len(names), -1)
+        n_ranks = ranks.shape[1]
+    rvals = np.full((len(names), n_ranks), np.nan, np.float64)
     res = {}
     groups = {}
-    for nme in names:
+    for i, nme in enumerate(names):
         kb = 32 if frame.column(nme).anv_dtype in (_lib.ANV_F32, _lib.ANV_I32) else 64
-        groups.setdefault(kb, []).append(nme)
-    for kb, grp in groups.items():
+        groups.setdefault(kb, []).append(i)
+    for kb, idxs in groups.items():
         per_col = L.anv_mode_distinct_workspace_bytes(1, frame.n_rows, kb)
         free = torch.cuda.mem_get_info()[0]
         budget = min(SORT_WORKSPACE_BUDGET, int(free * 0.8))
-        batch = max(1, min(len(grp), budget // max(per_col, 1)))
-        for b0 in range(0, len(grp), batch):
-            sub = grp[b0:b0 + batch]
+        batch = max(1, min(len(idxs), budget // max(per_col, 1)))
+        for b0 in range(0, len(idxs), batch):
+            sub_i = idxs[b0:b0 + batch]
+            sub = [names[i] for i in sub_i]
             desc, keep = frame.descriptors(sub)
             ws_bytes = L.anv_mode_distinct_workspace_bytes(len(sub), frame.n_rows, kb)
             ws = _dev_bytes(ws_bytes)
             n = len(sub)
             mv, mr, nd = _dev_bytes(n * 8), _dev_bytes(n * 8), _dev_bytes(n * 8)
+            drk = _to_dev(ranks[sub_i]) if n_ranks else None
+            drv = _dev_bytes(n * n_ranks * 8) if n_ranks else None
             _call(L.anv_mode_distinct, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv.data_ptr(), mr.data_ptr(),
-                                           nd.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+                  nd.data_ptr(), drk.data_ptr() if drk is not None else None, n_ranks,
+                  drv.data_ptr() if drv is not None else None, ws.data_ptr(), ws_bytes, _stream())
             launch_count += 3 + 3 * (kb // 8)
             hv = _host(mv).view(np.float64)[:n]
             hr = _host(mr).view(np.int64)[:n]
             hd = _host(nd).view(np.int64)[:n]
+            if n_ranks:
+                rvals[sub_i] = _host(drv).view(np.float64)[:n * n_ranks].reshape(n, n_ranks)
             del ws
-            for i, nme in enumerate(sub):
-                res[nme] = (float(hv[i]), int(hr[i]), int(hd[i])) if hr[i] > 0 else (None, None, 0)
-    return [res[n] for n in names]
+            for j, nme in enumerate(sub):
+                res[nme] = (float(hv[j]), int(hr[j]), int(hd[j])) if hr[j] > 0 else (None, None, 0)
+    out = [res[n] for n in names]
+    return (out, rvals) if ranks is not None else out
 
 
 # ---- HLL++ -------------------------------------------------------------------------------------

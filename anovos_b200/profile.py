@@ -93,8 +93,17 @@ def mode_distinct(frame: ColumnFrame, names):
             best = min((dic[i] for i in np.flatnonzero(h == mx)), key=lambda s: s.encode("utf-8"))
             c[n] = (best, mx, int(np.count_nonzero(h)))
     if num:
-        for n, r in zip(num, engine.sort_mode_distinct(frame, num)):
-            c[n] = r
+        # the sort leaves the keys fully ordered: read the summary() percentiles out of it as
+        # well, so a full stats_generator run never needs a separate selection pass
+        mom = moments(frame, num)
+        qc = _cache(frame, "quantiles")
+        rk = np.array([engine.quantile_ranks(int(mom[n]["n_valid"]), SUMMARY_PROBS) for n in num], dtype=np.int64)
+        res, vals = engine.sort_mode_distinct(frame, num, rk)
+        for i, n in enumerate(num):
+            c[n] = res[i]
+            for r, v in zip(rk[i], vals[i]):
+                if r:
+                    qc[(n, int(r))] = float(v)
     return {n: c[n] for n in names}
 
 

@@ -161,11 +161,14 @@ int anv_xxh64_utf8(const uint8_t* bytes, const int64_t* offsets, int64_t n, uint
  *      radix sort of the non-null values' order-preserving keys + run-length summary.
  * key_bits 32 (all columns F32/I32) or 64.  Outputs [dev] n_cols each: mode_value (NaN when
  * the column has no non-null value; ties -> smallest value), mode_rows, n_distinct
- * (-0.0 == 0.0, all NaNs equal). */
+ * (-0.0 == 0.0, all NaNs equal).  Since the keys end up fully sorted, exact order statistics
+ * are free: ranks [dev] n_cols * n_ranks 1-based ranks among the non-null values (0 = skip,
+ * n_ranks may be 0) -> rank_values [dev] n_cols * n_ranks (the summary() percentiles of
+ * stats_generator.py:488,813,908 without a separate selection pass). */
 size_t anv_mode_distinct_workspace_bytes(int n_cols, int64_t n_rows, int key_bits);
 int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, int key_bits,
-                      double* mode_value, int64_t* mode_rows, int64_t* n_distinct, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      double* mode_value, int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks,
+                      int n_ranks, double* rank_values, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- synthetic column generator used by bench.py / tests: Philox4x32-10
  *      keyed by (seed, column), counter = row.  family: 0 normal(a,b) 1 lognormal(0,b)

@@ -202,7 +202,18 @@ def test_mode_distinct_exact(n):
     t = t.append_column("f32_signed", pa.array(np.round(rng.normal(0, 3, n)).astype(np.float32)))
     fr = ColumnFrame.from_arrow(t)
     names = t.column_names
-    got = engine.sort_mode_distinct(fr, names)
+    probs = [0.01, 0.25, 0.5, 0.75, 0.99, 1.0]
+    rk = []
+    for c in names:
+        vals, valid = S.column_values(t, c)
+        rk.append(engine.quantile_ranks(int(valid.sum()), probs))
+    got, qv = engine.sort_mode_distinct(fr, names, np.array(rk))
+    for i, c in enumerate(names):   # order statistics read from the sorted keys
+        vals, valid = S.column_values(t, c)
+        srt = np.sort(vals[valid].astype(np.float64))
+        exp = [srt[r - 1] if r else np.nan for r in rk[i]]
+        assert np.array_equal(qv[i], np.array(exp), equal_nan=True), c
+    assert got == engine.sort_mode_distinct(fr, names)
     for c, (mode, rows, nd) in zip(names, got):
         vals, valid = S.column_values(t, c)
         x = vals[valid]
