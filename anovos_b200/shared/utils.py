@@ -39,7 +39,7 @@ def spark_round(x, scale=4):
     if scale == 4:
         # fast path: away from a decimal tie every correct rounding agrees with HALF_UP on the repr
         t = x * 10000.0
-        if abs(t) < 1e11 and abs((t - math.floor(t)) - 0.5) > 1e-6:
+        if abs(t) < 1e11 and abs((t - math.floor(t)) - 0.5) > 1e-6 + abs(t) * 2e-15:
             return round(x, 4)
     q = _QUANT.get(scale)
     if q is None:
