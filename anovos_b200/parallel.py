@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing of the hot path: columns are independent in every
+function of the path, so they shard across ranks with NO data-path collective; the only
+exchange is one all_gather of the small per-column summary table at the end of a pass
+(NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_columns(names, rank: int, world: int):
+    """Contiguous column blocks, ceil(C / world) per rank (source and target of a column stay
+    on the same rank, so drift needs no exchange)."""
+    names = list(names)
+    per = (len(names) + world - 1) // world
+    return names[rank * per:(rank + 1) * per]
+
+
+def frames_to_matrix(frames):
+    """Result frames (pandas) -> float64 matrix [n_attributes, n_numeric_fields] + the field names.
+    Non-numeric fields (attribute, mode) stay local to the rank; they are re-attached by name."""
+    import pandas as pd
+    cols, names = [], []
+    for df in frames:
+        num = df.drop(columns=[c for c in df.columns if c in ("attribute", "mode", "metric", "value")])
+        cols.append(num.apply(pd.to_numeric, errors="coerce").to_numpy(dtype=np.float64))
+        names += list(num.columns)
+    return np.ascontiguousarray(np.concatenate(cols, axis=1)), names
+
+
+def gather_summaries(matrix: np.ndarray, device=None):
+    """all_gather of each rank's [n_local_cols, n_fields] summary matrix -> list over ranks.
+    Ranks may own different numbers of columns: matrices are padded to the largest."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    t = torch.from_numpy(np.ascontiguousarray(matrix, dtype=np.float64))
+    if device is not None:
+        t = t.to(device)
+    n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local)
+    n_max = int(max(int(c.item()) for c in counts))
+    pad = torch.full((n_max, t.shape[1]), float("nan"), dtype=torch.float64, device=t.device)
+    pad[:t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return [o[:int(c.item())].cpu().numpy() for o, c in zip(out, counts)]

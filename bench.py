@@ -109,22 +109,11 @@ def stats_step(frame):
     return [o.toPandas() for o in out]
 
 
-def summary_tensor(frames, torch):
-    """Fixed-size per-column summary (float64) exchanged between ranks: SURVEY 8(e)."""
-    import numpy as np
-    import pandas as pd
-    cols = []
-    for df in frames:
-        num = df.drop(columns=[c for c in df.columns if c in ("attribute", "mode")])
-        cols.append(num.apply(pd.to_numeric, errors="coerce").to_numpy(dtype=np.float64))
-    return torch.from_numpy(np.ascontiguousarray(np.concatenate(cols, axis=1))).cuda()
-
-
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from anovos_b200 import engine, frame as framemod, synth
+    from anovos_b200 import engine, frame as framemod, parallel, synth
     from anovos_b200.frame import ColumnFrame
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,9 +138,8 @@ def run_ours(args):
     def step():
         frames = stats_step(src)
         if world > 1:  # the only exchange of the path: per-column summaries (tiny, latency-bound)
-            mine = summary_tensor(frames, torch)
-            gathered = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(gathered, mine)
+            mat, _ = parallel.frames_to_matrix(frames)
+            parallel.gather_summaries(mat, device="cuda")
         return frames
 
     if not args.no_extras:
@@ -190,9 +178,16 @@ def run_ours(args):
     peak, peak_src = peaks()
     k1_ms = k1["ms"] / max(k1["calls"], 1)
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    traffic = None
+    try:  # dram__bytes_read+write per launch from the committed `ncu --set full` capture (same workload only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tj.get("rows") == rows and tj.get("cols") == cols:
+            traffic = tj["dram_bytes_per_launch"].get("anv_moments")
+    except Exception:
+        pass
     roofline = {"kernel": "scan_kernel<MOM> (anv_moments: count/nonzero/min/max/mean/M2/M3/M4, FP64)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": None,
+                "frac": achieved / peak if achieved else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k1_ms,
                 "share_of_step": k1["ms"] / ms if ms > 0 else None}
     kernels = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
