@@ -21,7 +21,9 @@
 
 namespace anv {
 
-constexpr int SORT_TILE = 4096;  // keys per CTA (8 warps x 16 rounds x 32 lanes)
+constexpr int SORT_TILE = 4096;  // keys per CTA
+constexpr int SCAT_THREADS = 512;  // the scatter kernel runs 16 warps x 8 rounds of 32 keys
+constexpr int SCAT_WARPS = SCAT_THREADS / 32;
 
 template <typename K, typename T> __device__ __forceinline__ K make_key(T x);
 template <> __device__ __forceinline__ uint32_t make_key<uint32_t, float>(float x) {
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_hist_kernel(const SortParams<K
   h[tid] = 0;
   __syncthreads();
   if (t0 < n) {
-    const K* __restrict__ keys = P.buf[S.cur] + (size_t)c * P.stride + t0;
+    const K* __restrict__ keys = (S.cur ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride + t0;
     const int nt = (int)min((int64_t)SORT_TILE, n - t0);
     constexpr int KV = 16 / sizeof(K);  // keys per 128-bit load
     const int nvec = nt / KV;
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortParams<K> P) 
 // round by round.  The tile is then REORDERED IN SHARED MEMORY into digit order, so the global
 // writes are coalesced runs (full 32-byte sectors) instead of 4-byte scatters.
 template <typename K>
-__global__ void __launch_bounds__(ANV_BLOCK) sort_scatter_kernel(const SortParams<K> P) {
+__global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const SortParams<K> P) {
   const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ColState& S = P.state[c];
   if (S.skip[P.pass]) return;
@@ -286,19 +288,19 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_scatter_kernel(const SortParam
   if (t0 >= n) return;
   const int nt = (int)min((int64_t)SORT_TILE, n - t0);
   const int src = S.src[P.pass];
-  const K* __restrict__ in = P.buf[src] + (size_t)c * P.stride + t0;
-  K* __restrict__ out = P.buf[src ^ 1] + (size_t)c * P.stride;
-  __shared__ uint32_t wcnt[ANV_WARPS][256];
+  const K* __restrict__ in = (src ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride + t0;
+  K* __restrict__ out = (src ? P.buf[0] : P.buf[1]) + (size_t)c * P.stride;
+  __shared__ uint16_t wcnt[SCAT_WARPS][256];  // <= 4096 keys per tile: 16 bits are enough
   __shared__ uint32_t gbase[256];
   __shared__ uint32_t dstart[256];
-  __shared__ uint32_t wtot[ANV_WARPS];
+  __shared__ uint32_t wtot[8];
   __shared__ K sk[SORT_TILE];
-  for (int i = tid; i < ANV_WARPS * 256; i += ANV_BLOCK) (&wcnt[0][0])[i] = 0;
-  gbase[tid] = P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile];
-  constexpr int WR = SORT_TILE / ANV_WARPS / 32;  // 16 rounds per warp
+  for (int i = tid; i < SCAT_WARPS * 256 / 2; i += SCAT_THREADS) reinterpret_cast<uint32_t*>(&wcnt[0][0])[i] = 0;
+  if (tid < 256) gbase[tid] = P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile];
+  constexpr int WR = SORT_TILE / SCAT_WARPS / 32;  // 8 rounds per warp
   K key[WR];
   uint32_t peers[WR];
-  const int w0 = warp * (SORT_TILE / ANV_WARPS);
+  const int w0 = warp * (SORT_TILE / SCAT_WARPS);
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
     const int i = w0 + r * 32 + lane;
@@ -329,15 +331,15 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_scatter_kernel(const SortParam
     if (m) before = wcnt[warp][d];
     pos[r] = before + __popc(m & lt);
     __syncwarp();
-    if (m && lane == __ffs(m) - 1) wcnt[warp][d] = before + __popc(m);
+    if (m && lane == __ffs(m) - 1) wcnt[warp][d] = (uint16_t)(before + __popc(m));
     __syncwarp();
   }
   __syncthreads();
-  uint32_t total;
-  {  // exclusive prefix over warps for digit `tid`, tile total of the digit
+  uint32_t total = 0;
+  if (tid < 256) {  // exclusive prefix over warps for digit `tid`, tile total of the digit
     uint32_t acc = 0;
 #pragma unroll
-    for (int w = 0; w < ANV_WARPS; ++w) { const uint32_t t = wcnt[w][tid]; wcnt[w][tid] = acc; acc += t; }
+    for (int w = 0; w < SCAT_WARPS; ++w) { const uint32_t t = wcnt[w][tid]; wcnt[w][tid] = (uint16_t)acc; acc += t; }
     total = acc;
   }
   {  // exclusive scan of the 256 digit totals -> start of each digit inside the reordered tile
@@ -347,12 +349,14 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_scatter_kernel(const SortParam
       const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o);
       if (lane >= o) inc += t;
     }
-    if (lane == 31) wtot[warp] = inc;
+    if (lane == 31 && warp < 8) wtot[warp] = inc;
     __syncthreads();
-    uint32_t woff = 0;
+    if (tid < 256) {
+      uint32_t woff = 0;
 #pragma unroll
-    for (int w = 0; w < ANV_WARPS; ++w) woff += (w < warp) ? wtot[w] : 0u;
-    dstart[tid] = woff + inc - total;
+      for (int w = 0; w < 8; ++w) woff += (w < warp) ? wtot[w] : 0u;
+      dstart[tid] = woff + inc - total;
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_scatter_kernel(const SortParam
     }
   }
   __syncthreads();
-  for (int p = tid; p < nt; p += ANV_BLOCK) {
+  for (int p = tid; p < nt; p += SCAT_THREADS) {
     const K k = sk[p];
     const uint32_t d = digit_of(k, P.pass);
     out[(size_t)gbase[d] + (p - dstart[d])] = k;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K>
   TileSummary<K>& out = P.summ[(size_t)c * P.n_tiles + tile];
   if (t0 >= n) { if (tid == 0) out.n = 0; return; }
   const int nt = (int)min((int64_t)SORT_TILE, n - t0);
-  const K* __restrict__ keys = P.buf[S.cur] + (size_t)c * P.stride + t0;
+  const K* __restrict__ keys = (S.cur ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride + t0;
   __shared__ K sk[SORT_TILE];
   __shared__ unsigned long long s_best;
   __shared__ uint32_t s_heads, s_prefix, s_suffix;
@@ -473,7 +477,7 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
   const ColState& S = P.state[c];
   const int64_t n = (int64_t)S.n_valid;
   const int dt = P.cols[c].dtype;
-  const K* __restrict__ sorted = P.buf[S.cur] + (size_t)c * P.stride;
+  const K* __restrict__ sorted = (S.cur ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride;
   for (int r = lane; r < n_ranks; r += 32) {
     const int64_t rk = ranks[(size_t)c * n_ranks + r];
     double v = nan("");
@@ -558,7 +562,7 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
       P.pass = pass;
       sort_hist_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
       sort_scan_kernel<K><<<n_cols, 1024, 0, st>>>(P);
-      sort_scatter_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
+      sort_scatter_kernel<K><<<grid, SCAT_THREADS, 0, st>>>(P);
       ANV_CUDA(cudaGetLastError());
     }
     run_tile_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);

@@ -370,8 +370,9 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
         groups.setdefault(kb, []).append(i)
     for kb, idxs in groups.items():
         per_col = L.anv_mode_distinct_workspace_bytes(1, frame.n_rows, kb)
-        free = torch.cuda.mem_get_info()[0]
-        budget = min(SORT_WORKSPACE_BUDGET, int(free * 0.8))
+        budget = SORT_WORKSPACE_BUDGET
+        if per_col * len(idxs) > (4 << 30):  # cudaMemGetInfo costs ~7 ms: only ask when the scratch is large
+            budget = min(budget, int(torch.cuda.mem_get_info()[0] * 0.8))
         batch = max(1, min(len(idxs), budget // max(per_col, 1)))
         for b0 in range(0, len(idxs), batch):
             sub_i = idxs[b0:b0 + batch]
