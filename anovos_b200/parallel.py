@@ -18,11 +18,10 @@ def shard_columns(names, rank: int, world: int):
 def frames_to_matrix(frames):
     """Result frames (pandas) -> float64 matrix [n_attributes, n_numeric_fields] + the field names.
     Non-numeric fields (attribute, mode) stay local to the rank; they are re-attached by name."""
-    import pandas as pd
     cols, names = [], []
     for df in frames:
         num = df.drop(columns=[c for c in df.columns if c in ("attribute", "mode", "metric", "value")])
-        cols.append(num.apply(pd.to_numeric, errors="coerce").to_numpy(dtype=np.float64))
+        cols.append(num.to_numpy(dtype=np.float64, na_value=np.nan))
         names += list(num.columns)
     return np.ascontiguousarray(np.concatenate(cols, axis=1)), names
 

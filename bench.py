@@ -109,7 +109,31 @@ def stats_step(frame):
     return [o.toPandas() for o in out]
 
 
+class StdoutGuard:
+    """Route everything that libraries print on fd 1 (e.g. NCCL's version banner) to stderr, so
+    that stdout carries exactly ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_ours(args):
+    with StdoutGuard() as out:
+        _run_ours(args, out)
+
+
+def _run_ours(args, out):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -121,7 +145,6 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
     rows, cols = args.rows or wl["rows"], args.cols or wl["cols"]
@@ -204,7 +227,11 @@ def run_ours(args):
             except Exception as ex:  # never lose the main line
                 extra = {"error": repr(ex)}
             # ---- e2e: same step from pinned HOST buffers through the public API ---------------------
-            e2e = e2e_numbers(args, rows, cols, rank, torch, framemod, engine, src)
+            host = host_copy(src, torch)
+            src = None   # free the resident frame: at c3 (80 GB) it would not fit twice
+            torch.cuda.empty_cache()
+            e2e = e2e_numbers(args, rows, cols, host, torch, framemod, engine)
+            del host
             cpu = cpu_baseline(cols, with_drift=False)
         line = {"metric": METRIC, "value": value, "unit": "rows*cols/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -219,7 +246,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
 
 
 def fused_pass_numbers(src, rows, cols, alg_bytes, peak, torch, engine):
@@ -251,9 +278,8 @@ def fused_pass_numbers(src, rows, cols, alg_bytes, peak, torch, engine):
     return out
 
 
-def e2e_numbers(args, rows, cols, rank, torch, framemod, engine, src):
-    """Full step from pinned host buffers: H2D of every column + the result read-back inside
-    the timed region, through ColumnFrame.from_tensors + the stats_generator API."""
+def host_copy(src, torch):
+    """Pinned host copy of every column (+ validity words) of a device frame."""
     host = {}
     for name in src.columns:
         c = src.column(name)
@@ -266,11 +292,19 @@ def e2e_numbers(args, rows, cols, rank, torch, framemod, engine, src):
             hv.copy_(v)
         host[name] = (hd, hv) if hv is not None else hd
     torch.cuda.synchronize()
-    steps = max(1, min(args.steps, 5))
+    return host
+
+
+def e2e_numbers(args, rows, cols, host, torch, framemod, engine):
+    """Full step from pinned host buffers: H2D of every column + the result read-back inside
+    the timed region, through ColumnFrame.from_tensors + the stats_generator API."""
+    steps = max(1, min(args.steps, 5 if rows * cols <= 2_000_000_000 else 2))
 
     def one():
         fr = framemod.ColumnFrame.from_tensors(host, n_rows=rows)
-        return stats_step(fr)
+        r = stats_step(fr)
+        del fr
+        return r
 
     one()
     torch.cuda.synchronize()
