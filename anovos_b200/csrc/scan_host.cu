@@ -58,7 +58,7 @@ size_t hist_smem(int count_stride, int* path, int* thr_slots, bool codes) {
   while (p2 < nb) p2 <<= 1;
   *thr_slots = codes ? 2 : p2 + 2;  // dictionary codes need no thresholds
   size_t thr = (size_t)(*thr_slots) * 8;
-  if (count_stride <= 40) { *path = 0; return thr + (size_t)count_stride * ANV_BLOCK * 4; }
+  if (count_stride <= 40) { *path = 0; return thr + 2 * (size_t)count_stride * ANV_BLOCK * 4; }  // counters + per-thread threshold replica
   if (count_stride <= 10240) { *path = 1; return thr + (size_t)count_stride * 4; }
   *path = 2;
   return thr;

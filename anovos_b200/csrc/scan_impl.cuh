@@ -61,6 +61,9 @@ template <bool MOM, int HPATH, bool ASSIGN> struct Tune {
 #else
   static constexpr int MINB = 4;
 #endif
+  // software pipelining (loads of half-batch k+1 in flight while half-batch k is consumed) pays for
+  // the histogram-only kernel (+13 %); with the FP64 moments it only adds register pressure
+  static constexpr bool PF = !MOM && HPATH == 0 && !ASSIGN;
 };
 
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
@@ -115,27 +118,38 @@ template <> __device__ __forceinline__ int Binner<double, BIN_GUESS>::slot(doubl
 }
 
 // Fast float32 equal_range path of the private-counter histogram.  Everything is expressed
-// on the raw bits of a float that carries the (reversed) bin guess, so the threshold lookup and
-// the counter address are ONE multiply-add each (32-bit shared-window addresses, inline PTX)
-// and there is no min/max clamp (FFMA.SAT saturates for free, and maps NaN to 0):
+// on the raw bits of a float that carries the (reversed) bin guess, and the exact threshold of
+// every slot is REPLICATED PER THREAD right behind the private counters (same [slot][tid]
+// layout, bank = lane: conflict-free), so one multiply-add yields the address of both:
 //   v    = sat(1 - (x - lo) * c)            c = inv_w / (B-1);   NaN, +inf -> 0;  -inf -> 1
 //   r'   = round(v * (B-1)) = bits(v * (B-1) + 1.5*2^23) - 0x4B400000      (= B-1-r)
-//   slot = (B-1-r') + !(x <= Srev[r'])      Srev[j] = S[B-1-j]; S[0] = NaN => slot >= 1;
-//                                           NaN x => r' = 0, compare false => slot = B
-//   addr = cnt_t + slot * 1024
+//   a0   = cnt_t + (B-1-r') * 1024          counter of slot r = B-1-r'      (ONE IMAD)
+//   th   = [a0 + toff]                      = S[r]: theta_{r-1}; S[0] = NaN (ONE LDS, immediate offset)
+//   a    = a0 + (x > th or unordered ? 1024 : 0)   => slot = r + !(x <= th)  (setp + predicated add)
+//   red.shared.add [a], 1                   NaN x: r' = 0, compare unordered => slot = B
+// FFMA.SAT saturates for free (no min/max clamp) and maps NaN to 0.
 struct FastF32 {
-  uint32_t s_adj, c_adj;
+  uint32_t c_adj, toff;
   float lo, negc, bm1;
   __device__ __forceinline__ uint32_t counter_addr(float x) const {
     float v;
     asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(v) : "f"(x - lo), "f"(negc), "f"(1.0f));
     const uint32_t bits = __float_as_uint(fmaf(v, bm1, 12582912.0f));
-    const float th = lds_f32(s_adj + (bits << 2));
     uint32_t a = c_adj - (bits << 10);
-    if (!(x <= th)) a += ANV_BLOCK * 4;
+    const float th = lds_f32(a + toff);
+    asm("{\n\t.reg .pred p;\n\tsetp.gtu.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 1024;\n\t}" : "+r"(a) : "f"(x), "f"(th));
     return a;
   }
 };
+
+// n += (x != 0) as compare + predicated add (2 instructions; the C++ form costs a third, a select)
+template <typename T> __device__ __forceinline__ void count_nonzero(uint32_t& n, T x) { n += (x != (T)0) ? 1u : 0u; }
+template <> __device__ __forceinline__ void count_nonzero<float>(uint32_t& n, float x) {
+  asm("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, 0f00000000;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(n) : "f"(x));
+}
+template <> __device__ __forceinline__ void count_nonzero<int32_t>(uint32_t& n, int32_t x) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(n) : "r"(x));
+}
 
 // 3-input min / max (FMNMX3 / VIMNMX3 on sm_100a): one instruction per two elements.
 __device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
@@ -215,11 +229,10 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   uint32_t cnt_t_saddr = 0;
   if (HPATH == 0) cnt_t_saddr = (uint32_t)__cvta_generic_to_shared(cnt_t);
   if (FAST) {
-    // reversed thresholds live in the free upper half of the 8-byte threshold slots
-    float* Srev = reinterpret_cast<float*>(smem) + (bn.P + 2);
-    for (int j = tid; j < bn.B; j += ANV_BLOCK) Srev[j] = reinterpret_cast<const float*>(smem)[bn.B - 1 - j];
-    __syncthreads();
-    ff.s_adj = (uint32_t)__cvta_generic_to_shared(Srev) - (0x4B400000u << 2);
+    // per-thread replica of the thresholds, [slot][tid] right behind the counters (this thread's own words)
+    ff.toff = (uint32_t)P.count_stride * ANV_BLOCK * 4;
+    float* rep = reinterpret_cast<float*>(cnt_t) + (size_t)P.count_stride * ANV_BLOCK;
+    for (int r = 0; r < bn.B; ++r) rep[r * ANV_BLOCK] = reinterpret_cast<const float*>(smem)[r];
     ff.c_adj = cnt_t_saddr + ((uint32_t)(bn.B - 1) << 10) + (0x4B400000u << 10);
     ff.lo = (float)bn.lo; ff.bm1 = (float)(bn.B - 1); ff.negc = -((float)bn.invw / ff.bm1);
   }
@@ -275,7 +288,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
       s2 += d2;
       s3 = fma(d2, d, s3);
       s4 = fma(d2, d2, s4);
-      n_nz += (x != (T)0) ? 1u : 0u;
+      count_nonzero<T>(n_nz, x);
     }
     if (FAST) {
       red_shared_inc(ff.counter_addr(*reinterpret_cast<const float*>(&x)));
@@ -319,6 +332,48 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   const uint4* __restrict__ vdata = reinterpret_cast<const uint4*>(data);
   const int vsh = (tid * VEC) & 31;  // bit offset of this thread's vector inside its bitmap word (loop-invariant)
   int base = 0;
+  if constexpr (Tune<MOM, HPATH, ASSIGN>::PF) {
+  // software pipeline: the loads of batch k+1 are in flight while batch k is consumed
+  constexpr int HB = UNROLL / 2;  // vectors per half batch
+  constexpr int STEP = ANV_BLOCK * HB;
+  auto load_half = [&](int b, uint4 (&q)[HB], uint32_t (&vb)[HB]) {
+    const uint4* p = vdata + b + tid;
+    const uint32_t* wp = NULLS ? vwords + (((b + tid) * VEC) >> 5) : nullptr;
+#pragma unroll
+    for (int u = 0; u < HB; ++u) {
+      q[u] = ldg_stream(p + u * ANV_BLOCK);
+      if (NULLS) vb[u] = (__ldg(wp + u * WSTEP) >> vsh) & VMASK;
+    }
+  };
+  auto use_half = [&](int b, const uint4 (&q)[HB], const uint32_t (&vb)[HB]) {
+#pragma unroll
+    for (int u = 0; u < HB; ++u) {
+      T e[VEC];
+      unpack<T>(q[u], e);
+      int sl[VEC];
+      vec(e, NULLS ? vb[u] : VMASK, sl);
+      if (ASSIGN) store_bins((b + u * ANV_BLOCK + tid) * VEC, sl);
+    }
+  };
+  if (STEP <= nvec) {
+    uint4 qa[HB], qb[HB];
+    uint32_t va[HB], vbb[HB];
+    load_half(0, qa, va);
+    // invariant at the top: qa holds the unconsumed half batch at `base` (all conditions are CTA-uniform)
+    while (true) {
+      const bool more_b = base + 2 * STEP <= nvec;
+      if (more_b) load_half(base + STEP, qb, vbb);
+      use_half(base, qa, va);
+      base += STEP;
+      if (!more_b) break;
+      const bool more_a = base + 2 * STEP <= nvec;
+      if (more_a) load_half(base + STEP, qa, va);
+      use_half(base, qb, vbb);
+      base += STEP;
+      if (!more_a) break;
+    }
+  }
+  } else {
   for (; base + ANV_BLOCK * UNROLL <= nvec; base += ANV_BLOCK * UNROLL) {
     uint4 q[UNROLL];
     uint32_t vb[UNROLL];
@@ -337,6 +392,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
       vec(e, NULLS ? vb[u] : VMASK, sl);
       if (ASSIGN) store_bins((base + u * ANV_BLOCK + tid) * VEC, sl);
     }
+  }
   }
   for (int j = base + tid; j < nvec; j += ANV_BLOCK) {  // remainder vectors
     const uint4 q = ldg_stream(vdata + j);
