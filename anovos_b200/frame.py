@@ -97,7 +97,7 @@ def _arrow_validity_words(arr):
 
 class Column:
     __slots__ = ("name", "sdtype", "kind", "anv_dtype", "n_rows", "null_count", "dictionary",
-                 "_host", "_host_valid", "_dev", "_dev_valid")
+                 "_host", "_host_valid", "_dev", "_dev_valid", "_ready")
 
     def __init__(self, name, sdtype, n_rows, host=None, host_valid=None, dev=None, dev_valid=None,
                  anv_dtype=None, null_count=None, dictionary=None):
@@ -107,6 +107,36 @@ class Column:
         self.anv_dtype = anv_dtype
         self.null_count = null_count
         self.dictionary = dictionary
+        self._ready = None  # CUDA event of an in-flight asynchronous upload
+
+    def upload_async(self, stream):
+        """Enqueue the H2D copy of this column on `stream` (pinned host memory makes it truly
+        asynchronous); consumers wait on the recorded event, not on the host."""
+        global h2d_bytes
+        torch = _lib.require_cuda()
+        if self._dev is not None or self.kind == "other" or self._host is None:
+            return
+        h = self._host if self._host.flags.writeable else self._host.copy()
+        th = torch.from_numpy(h)
+        dv = None
+        consumer = torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            # allocate from the copy stream's pool (blocks are reused by the next upload without a
+            # cudaMalloc) and tell the allocator that the compute stream uses them too
+            dev = torch.empty(th.shape, dtype=th.dtype, device="cuda")
+            dev.copy_(th, non_blocking=True)
+            h2d_bytes += h.nbytes
+            if self._host_valid is not None:
+                tv = torch.from_numpy(self._host_valid)
+                dv = torch.empty(tv.shape, dtype=tv.dtype, device="cuda")
+                dv.copy_(tv, non_blocking=True)
+                h2d_bytes += self._host_valid.nbytes
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        dev.record_stream(consumer)
+        if dv is not None:
+            dv.record_stream(consumer)
+        self._dev, self._dev_valid, self._ready = dev, dv, ev
 
     @property
     def has_validity(self):
@@ -117,6 +147,9 @@ class Column:
         torch = _lib.require_cuda()
         if self.kind == "other":
             raise _lib.AnvError("column %r has dtype %s which the hot path does not process" % (self.name, self.sdtype))
+        if self._ready is not None:  # asynchronous upload in flight: order the current stream after it
+            torch.cuda.current_stream().wait_event(self._ready)
+            self._ready = None
         if self._dev is None:
             global h2d_bytes
             h = self._host if self._host.flags.writeable else self._host.copy()

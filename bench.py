@@ -99,10 +99,11 @@ class ClockSampler:
 # the step
 # ---------------------------------------------------------------------------------------------
 
-def stats_step(frame):
+def stats_step(frame, keep_cache=False):
     """Full stats_generator through the public API; returns the result frames (pandas)."""
     import anovos.data_analyzer.stats_generator as sg
-    frame._cache = {k: v for k, v in frame._cache.items() if isinstance(k, tuple) and k and k[0] == "desc"}
+    if not keep_cache:
+        frame._cache = {k: v for k, v in frame._cache.items() if isinstance(k, tuple) and k and k[0] == "desc"}
     out = [sg.measures_of_counts(None, frame), sg.measures_of_centralTendency(None, frame),
            sg.measures_of_cardinality(None, frame), sg.measures_of_dispersion(None, frame),
            sg.measures_of_percentiles(None, frame), sg.measures_of_shape(None, frame)]
@@ -300,9 +301,12 @@ def e2e_numbers(args, rows, cols, host, torch, framemod, engine):
     the timed region, through ColumnFrame.from_tensors + the stats_generator API."""
     steps = max(1, min(args.steps, 5 if rows * cols <= 2_000_000_000 else 2))
 
+    from anovos_b200 import profile
+
     def one():
         fr = framemod.ColumnFrame.from_tensors(host, n_rows=rows)
-        r = stats_step(fr)
+        profile.prefetch(fr)   # H2D of column group g+1 overlaps the passes over group g
+        r = stats_step(fr, keep_cache=True)
         del fr
         return r
 
@@ -316,7 +320,7 @@ def e2e_numbers(args, rows, cols, host, torch, framemod, engine):
     dt = (time.perf_counter() - t0) / steps
     return {"value": rows * cols / dt, "unit": "rows*cols/s", "ms_per_step": dt * 1e3,
             "h2d_bytes_per_step": (framemod.h2d_bytes - h0) // steps, "d2h_bytes_per_step": (engine.d2h_bytes - d0) // steps,
-            "steps": steps, "note": "pinned host columns -> H2D -> 6 measures_of_* -> pandas, wall clock incl. host post-processing"}
+            "steps": steps, "note": "pinned host columns -> pipelined H2D (profile.prefetch) -> 6 measures_of_* -> pandas, wall clock incl. host post-processing"}
 
 
 # ---------------------------------------------------------------------------------------------

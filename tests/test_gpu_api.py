@@ -362,3 +362,26 @@ def test_drift_vs_oracle(dd, tmp_path, n, bin_method, bins):
     again = dd.statistics(None, tgt, None, pre_existing_source=True, source_path=str(tmp_path / "g"), **kw).toPandas()
     for m in ("PSI", "HD", "JSD", "KS"):
         assert np.allclose(again[m].values.astype(float), got[m].values.astype(float), rtol=1e-9, atol=1e-12), m
+
+
+def test_prefetch_pipeline_matches_direct(sg):
+    """profile.prefetch (async grouped upload + passes) must give the same frames as the lazy path."""
+    import torch
+    from anovos_b200 import profile
+    from anovos_b200.frame import ColumnFrame
+    n = 300007
+    rng = np.random.default_rng(5)
+    host = {}
+    for i in range(7):
+        x = torch.from_numpy(rng.normal(i, 1 + i, n).astype(np.float32)).pin_memory()
+        valid = rng.random(n) > 0.1 * (i % 3)
+        bits = np.packbits(valid, bitorder="little")
+        bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, np.uint8)]).view(np.int32)
+        host["c%d" % i] = (x, torch.from_numpy(bits).pin_memory()) if i % 3 else x
+    a = ColumnFrame.from_tensors(host, n_rows=n)
+    b = ColumnFrame.from_tensors(host, n_rows=n)
+    profile.prefetch(b, group=3)
+    for f in (sg.measures_of_counts, sg.measures_of_centralTendency, sg.measures_of_cardinality,
+              sg.measures_of_dispersion, sg.measures_of_percentiles, sg.measures_of_shape):
+        x, y = f(None, a).toPandas(), f(None, b).toPandas()
+        assert x.equals(y), f.__name__
