@@ -68,8 +68,12 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise AnvError("libanovos_b200.so is not built (%s). Run `python -m anovos_b200.build` "
-                           "(needs nvcc). There is no CPU fallback." % LIB_PATH)
+            try:  # build in-tree when a CUDA toolkit is around; never fall back to a CPU path
+                from . import build as _build
+                _build.build()
+            except Exception as e:
+                raise AnvError("libanovos_b200.so is not built (%s) and building it failed (%s). Run "
+                               "`python -m anovos_b200.build` (needs nvcc). There is no CPU fallback." % (LIB_PATH, e))
         h = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             f = getattr(h, name)

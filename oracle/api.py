@@ -594,3 +594,114 @@ def statistics(idf_target, idf_source, *, list_of_cols="all", drop_cols=None, me
         dbg[c] = (src, tgt)
     out = pd.DataFrame(rows)
     return (out, dbg) if return_groups else out
+
+
+# ---------------------------------------------------------------------------
+# N1: stability_index_computation (drift_stability/stability.py:15-332, validations.py:97-172)
+# ---------------------------------------------------------------------------
+
+
+def compute_score(value, method_type, cv_thresholds=(0.03, 0.1, 0.2, 0.5)):
+    """validations.py:97-126."""
+    if value is None:
+        return None
+    if method_type == "cv":
+        cv = abs(value)
+        for i, th in enumerate(cv_thresholds):
+            if cv < th:
+                return float([4, 3, 2, 1, 0][i])
+        return 0.0
+    if method_type == "sd":
+        sd = value
+        if sd <= 0.005:
+            return 4.0
+        if sd <= 0.01:
+            return round(-100 * sd + 4.5, 1)
+        if sd <= 0.05:
+            return round(-50 * sd + 4, 1)
+        if sd <= 0.1:
+            return round(-30 * sd + 3, 1)
+        return 0.0
+    raise TypeError("method_type must be either 'cv' or 'sd'.")
+
+
+def _samp_std(vals):
+    vals = [v for v in vals if v is not None]
+    if len(vals) < 2:
+        return None
+    m = sum(vals) / len(vals)
+    return math.sqrt(sum((v - m) ** 2 for v in vals) / (len(vals) - 1))
+
+
+def _mean(vals):
+    vals = [v for v in vals if v is not None]
+    return sum(vals) / len(vals) if vals else None
+
+
+def _div(a, b):
+    if a is None or b is None or b == 0:
+        return None
+    return a / b
+
+
+def stability_index_computation(tables, list_of_cols="all", drop_cols=[], metric_weightages=None, binary_cols=[],
+                                existing_metric_path="", appended_metric_path="", threshold=1):
+    """stability.py:150-332 on a list of pyarrow Tables."""
+    metric_weightages = metric_weightages or {"mean": 0.5, "stddev": 0.3, "kurtosis": 0.2}
+    num = S.segregate(tables[0])[0]
+    cols = _resolve(tables[0], list_of_cols, drop_cols, num, universe=num)
+    binary_cols = _split(binary_cols)
+    if any(c not in cols for c in binary_cols):
+        raise TypeError("Invalid input for Binary Column(s)")
+    if round(sum(metric_weightages.get(k, 0) for k in ("mean", "stddev", "kurtosis")), 3) != 1:
+        raise ValueError("Invalid input for metric weightages. Either metric name is incorrect or sum of metric "
+                         "weightages is not 1.0.")
+    if threshold < 0 or threshold > 4:
+        raise ValueError("Invalid input for metric threshold. It must be a number between 0 and 4.")
+    existing = None
+    start = 1
+    if existing_metric_path:
+        files = sorted(f for f in os.listdir(existing_metric_path) if f.endswith(".csv"))
+        existing = pd.concat([pd.read_csv(os.path.join(existing_metric_path, f)) for f in files], ignore_index=True)
+        start = int(existing["idx"].max()) + 1
+    rows, appended = [], []
+    for c in cols:
+        ctype = "Binary" if c in binary_cols else "Numerical"
+        means, sds, kurts = [], [], []
+        for k, t in enumerate(tables):
+            p = ColumnProfile(t, c)
+            n, mean, m2, m3, m4 = S.central_moments(p.x64)
+            sd = S.stddev_samp(n, m2)
+            ku = S.kurtosis(n, m2, m4)
+            ku = None if ku is None else ku + 3
+            means.append(mean); sds.append(sd); kurts.append(ku)
+            appended.append([start + k, c, ctype, mean, sd, ku])
+        if existing is not None:
+            e = existing[existing["attribute"] == c]
+            means += [None if pd.isna(v) else float(v) for v in e["mean"]]
+            sds += [None if pd.isna(v) else float(v) for v in e["stddev"]]
+            kurts += [None if pd.isna(v) else float(v) for v in e["kurtosis"]]
+        mean_sd = _samp_std(means)
+        mean_cv = _div(mean_sd, _mean(means))
+        sd_cv = _div(_samp_std(sds), _mean(sds))
+        ku_cv = _div(_samp_std(kurts), _mean(kurts))
+        if ctype == "Binary":
+            mean_si = compute_score(mean_sd, "sd")
+            sd_si = ku_si = None
+            si = mean_si
+        else:
+            mean_si, sd_si, ku_si = compute_score(mean_cv, "cv"), compute_score(sd_cv, "cv"), compute_score(ku_cv, "cv")
+            si = None if None in (mean_si, sd_si, ku_si) else round(
+                mean_si * metric_weightages.get("mean", 0) + sd_si * metric_weightages.get("stddev", 0)
+                + ku_si * metric_weightages.get("kurtosis", 0), 4)
+        f32 = lambda v: None if v is None else float(np.float32(v))      # ArrayType(FloatType()) (:293)
+        rows.append([c, ctype, R(mean_sd), R(mean_cv), R(sd_cv), R(ku_cv), f32(mean_si), f32(sd_si), f32(ku_si), f32(si),
+                     int(si is None or si < threshold)])
+    if appended_metric_path:
+        os.makedirs(appended_metric_path, exist_ok=True)
+        df = pd.DataFrame(appended, columns=["idx", "attribute", "type", "mean", "stddev", "kurtosis"])
+        if existing is not None:
+            df = pd.concat([df, existing], ignore_index=True)
+        df.sort_values("idx", kind="stable").to_csv(os.path.join(appended_metric_path, "part-00000.csv"), index=False)
+    return pd.DataFrame(rows, columns=["attribute", "type", "mean_stddev", "mean_cv", "stddev_cv", "kurtosis_cv", "mean_si",
+                                       "stddev_si", "kurtosis_si", "stability_index", "flagged"])

@@ -10,6 +10,7 @@ reference stores in its notebooks, plus the input datasets they were computed on
                           notebooks do), typed like Spark's CSV inferSchema
   income_source.parquet   examples/data/income_dataset/source/sample1.csv (drift source)
   income_part1.parquet    data/test_dataset/part-00001-*.snappy.parquet (test_transformers.py:22)
+  stability.parquet       examples/data/income_dataset/stability_index/{0..11} stacked, column `_ds` = dataset id
   notebook_stats.json     stored outputs of examples/notebooks/data_analyzer__stats_generator.ipynb
   notebook_drift.json     stored outputs of examples/notebooks/drift_stability.ipynb
 """
@@ -97,6 +98,13 @@ def main():
     shutil.copyfile(REF + "/data/test_dataset/part-00001-3eb0f7bb-05c2-46ec-8913-23ba231d2734-c000.snappy.parquet",
                     OUT + "/income_part1.parquet")
     os.chmod(OUT + "/income_part1.parquet", 0o644)
+    parts = []
+    for ds in range(12):
+        d = REF + "/examples/data/income_dataset/stability_index/%d" % ds
+        f = [x for x in os.listdir(d) if x.endswith(".csv")][0]
+        t = pacsv.read_csv(os.path.join(d, f))
+        parts.append(t.append_column("_ds", pa.array([ds] * t.num_rows, pa.int32())))
+    pq.write_table(pa.concat_tables(parts, promote_options="default"), OUT + "/stability.parquet", compression="zstd")
     json.dump(notebook_tables(REF + "/examples/notebooks/data_analyzer__stats_generator.ipynb"),
               open(OUT + "/notebook_stats.json", "w"), indent=0)
     json.dump(notebook_tables(REF + "/examples/notebooks/drift_stability.ipynb"),

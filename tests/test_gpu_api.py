@@ -385,3 +385,35 @@ def test_prefetch_pipeline_matches_direct(sg):
               sg.measures_of_dispersion, sg.measures_of_percentiles, sg.measures_of_shape):
         x, y = f(None, a).toPandas(), f(None, b).toPandas()
         assert x.equals(y), f.__name__
+
+
+# ---- N1: stability_index_computation (drift_stability/test_stability.py:69-92, notebook cells 14-17) ---------
+
+def test_stability_index(tmp_path, nb_drift):
+    import anovos.drift_stability.stability as st
+    from test_oracle_golden import _stab_tables, check_stability_notebook
+    r = st.stability_index_computation(None, _stab_tables()).toPandas().iloc[0]
+    np.testing.assert_almost_equal([r[c] for c in ("mean_cv", "stddev_cv", "kurtosis_cv", "mean_si", "stddev_si", "kurtosis_si",
+                                                   "stability_index", "flagged")], [0.162, 0.62, 0.198, 2.0, 0.0, 2.0, 1.4, 0.0], 3)
+    b = [pa.table({"A": np.array([0] * z + [1] * (20 - z))}) for z in (10, 12, 14)]
+    r = st.stability_index_computation(None, b, binary_cols="A").toPandas().iloc[0]
+    np.testing.assert_almost_equal([r["mean_stddev"], r["mean_si"], r["stability_index"], r["flagged"]], [0.1, 0.0, 0.0, 1.0], 3)
+    with pytest.raises(ValueError):
+        st.stability_index_computation(None, _stab_tables(), metric_weightages={"mean": 0.5})
+    with pytest.raises(TypeError):
+        st.stability_index_computation(None, _stab_tables(), binary_cols="Z")
+    check_stability_notebook(lambda tables, **kw: st.stability_index_computation(None, tables, **kw).toPandas(), nb_drift, tmp_path)
+    # product == oracle on every column of the 12-dataset run
+    from test_oracle_golden import _stab_datasets
+    ds = _stab_datasets()
+    got = st.stability_index_computation(None, ds, threshold=2).toPandas()
+    exp = O.stability_index_computation(ds, threshold=2)
+    _cmp_frames(ResultLike(got), exp)
+
+
+class ResultLike:
+    def __init__(self, df):
+        self.df = df
+
+    def toPandas(self):
+        return self.df

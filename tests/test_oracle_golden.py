@@ -304,3 +304,60 @@ def test_xxh64_known_answers():
     b = np.array([1, -7, 1 << 40], dtype=np.int64)
     for v, h in zip(b.tolist(), S.xxh64_long_np(b).tolist()):
         assert h == S.xxh64_bytes(int(v).to_bytes(8, "little", signed=True))
+
+
+# ---- N1: drift_stability/test_stability.py:69-92 and notebook cells 16/17 --------------------------------
+
+def _stab_tables():
+    l1 = np.array([4.34, 4.76, 4.32, 3.39, 3.67, 4.61, 4.03, 4.93, 3.84, 3.31])
+    l2 = np.array([6.34, 4.76, 6.32, 3.39, 5.67, 4.61, 6.03, 4.93, 5.84, 3.31])
+    l3 = np.array([8.34, 4.76, 8.32, 3.39, 7.67, 4.61, 8.03, 4.93, 3.84, 3.31])
+    return [pa.table({"A": l}) for l in (l1, l2, l3)]
+
+
+def test_stability_index_known_answers():
+    r = O.stability_index_computation(_stab_tables()).iloc[0]
+    np.testing.assert_almost_equal([r[c] for c in ("mean_cv", "stddev_cv", "kurtosis_cv", "mean_si", "stddev_si", "kurtosis_si",
+                                                   "stability_index", "flagged")], [0.162, 0.62, 0.198, 2.0, 0.0, 2.0, 1.4, 0.0], 3)
+    b = [pa.table({"A": np.array([0] * z + [1] * (20 - z))}) for z in (10, 12, 14)]
+    r = O.stability_index_computation(b, binary_cols="A").iloc[0]
+    np.testing.assert_almost_equal([r["mean_stddev"], r["mean_si"], r["stability_index"], r["flagged"]], [0.1, 0.0, 0.0, 1.0], 3)
+    with pytest.raises(ValueError):
+        O.stability_index_computation(_stab_tables(), metric_weightages={"mean": 0.5})
+    with pytest.raises(ValueError):
+        O.stability_index_computation(_stab_tables(), threshold=5)
+    with pytest.raises(TypeError):
+        O.stability_index_computation(_stab_tables(), binary_cols="Z")
+
+
+def _stab_datasets():
+    import pyarrow.parquet as pq
+    import pyarrow.compute as pc
+    from conftest import GOLDEN
+    t = pq.read_table(GOLDEN + "/stability.parquet")
+    return [t.filter(pc.equal(t["_ds"], k)).drop_columns(["_ds"]) for k in range(12)]
+
+
+def check_stability_notebook(fn, nb_drift, tmp_path):
+    """Shared by the oracle and the product test: notebook cells 14-17 of drift_stability.ipynb.
+    (The stored stability_index column predates the current compute_si: it shows NaN whenever one
+    component score is 0, which the v1.1.0 code no longer does - those cells are skipped.)"""
+    ds = _stab_datasets()
+    p1, p5, p12 = str(tmp_path / "m1"), str(tmp_path / "m5"), str(tmp_path / "m12")
+    r1 = fn([ds[0]], appended_metric_path=p1)
+    assert r1["stability_index"].isna().all() and (r1["flagged"] == 1).all()       # one dataset: all null
+    r2 = fn(ds[1:5], existing_metric_path=p1, appended_metric_path=p5, threshold=2)
+    r3 = fn(ds[5:12], existing_metric_path=p5, appended_metric_path=p12, threshold=2)
+    for got, cell in ((r2, 16), (r3, 17)):
+        exp = table_by_attr(nb_drift[cell])
+        g = frame_by_attr(got)
+        assert set(g) == set(exp)
+        for a, row in exp.items():
+            for c in ("mean_stddev", "mean_cv", "stddev_cv", "kurtosis_cv", "mean_si", "stddev_si", "kurtosis_si"):
+                assert shown_close(g[a][c], row[c]), (cell, a, c, g[a][c], row[c])
+            if cell_value(row["stability_index"]) is not None:
+                assert shown_close(g[a]["stability_index"], row["stability_index"]) and g[a]["flagged"] == int(row["flagged"])
+
+
+def test_nb_stability_index(nb_drift, tmp_path):
+    check_stability_notebook(lambda tables, **kw: O.stability_index_computation(tables, **kw), nb_drift, tmp_path)
