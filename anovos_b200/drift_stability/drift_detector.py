@@ -36,13 +36,25 @@ def _freq_dir(model_path, col):
     return os.path.join(model_path, "frequency_counts", col)
 
 
+def _csv_field(v):
+    if v is None:
+        return ""
+    s = str(v)
+    if any(ch in s for ch in ',"\n\r'):
+        s = '"' + s.replace('"', '""') + '"'
+    return s
+
+
 def _save_frequency(model_path, col, keys, p):
+    """`x.coalesce(1).write.csv(.../frequency_counts/<col>, header=True, mode="overwrite")` (:257-262)."""
     d = _freq_dir(model_path, col)
     os.makedirs(d, exist_ok=True)
     for f in os.listdir(d):
         if f.endswith(".csv"):
             os.remove(os.path.join(d, f))
-    pd.DataFrame({col: keys, "p": p}).to_csv(os.path.join(d, "part-00000.csv"), index=False)
+    with open(os.path.join(d, "part-00000.csv"), "w", newline="") as fh:
+        fh.write(_csv_field(col) + ",p\n")
+        fh.write("".join("%s,%s\n" % (_csv_field(k), repr(float(v))) for k, v in zip(keys, p)))
 
 
 def _load_frequency(model_path, col):

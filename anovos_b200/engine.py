@@ -103,32 +103,27 @@ def moments(frame: ColumnFrame, names):
 
 # ---- binning model -> device specs ---------------------------------------------------------
 
-def _round_down_f32(c: float) -> np.float32:
-    if math.isnan(c):
-        return np.float32(-np.inf)  # `v <= NaN` is False for every v: the cutoff is "below" everything
-    with np.errstate(over="ignore"):
-        t = np.float32(c)
-    if float(t) > c:
-        t = np.nextafter(t, np.float32(-np.inf), dtype=np.float32)
-    return t
-
-
 def native_thresholds(cutoffs, anv_dtype) -> np.ndarray:
-    """float64 cutoffs -> native-type thresholds theta with (double(v) <= c) == (v <= theta), as uint64 slots."""
-    n = len(cutoffs)
-    raw = np.zeros(n, dtype=np.uint64)
+    """float64 cutoffs -> native-type thresholds theta with (double(v) <= c) == (v <= theta), as uint64 slots.
+    NaN cutoffs (`v <= NaN` is False for every v) become the lowest value: "below" everything."""
+    cut = np.asarray(cutoffs, dtype=np.float64)
+    raw = np.zeros(cut.size, dtype=np.uint64)
+    nan = np.isnan(cut)
     if anv_dtype == _lib.ANV_F32:
-        th = np.array([_round_down_f32(float(c)) for c in cutoffs], dtype=np.float32)
+        with np.errstate(over="ignore", invalid="ignore"):
+            th = cut.astype(np.float32)
+            up = th.astype(np.float64) > cut                      # rounded up: step one float32 down
+            th = np.where(up, np.nextafter(th, np.float32(-np.inf)), th).astype(np.float32)
+        th[nan] = -np.inf
         raw[:] = th.view(np.uint32).astype(np.uint64)
     elif anv_dtype == _lib.ANV_F64:
-        th = np.array([(-np.inf if math.isnan(float(c)) else float(c)) for c in cutoffs], dtype=np.float64)
+        th = np.where(nan, -np.inf, cut)
         raw[:] = th.view(np.uint64)
     else:
         lo, hi = (-(1 << 31), (1 << 31) - 1) if anv_dtype == _lib.ANV_I32 else (-(1 << 63), (1 << 63) - 1)
         vals = []
-        for c in cutoffs:
-            c = float(c)
-            if math.isnan(c) or c == -math.inf:
+        for c in cut.tolist():
+            if c != c or c == -math.inf:
                 v = lo
             elif c == math.inf:
                 v = hi

@@ -227,6 +227,10 @@ def _run_ours(args, out):
                 extra = fused_pass_numbers(src, rows, cols, alg_bytes, peak, torch, engine)
             except Exception as ex:  # never lose the main line
                 extra = {"error": repr(ex)}
+            try:
+                extra["drift_statistics"] = drift_numbers(args, src, rows, cols, rank, torch, engine, synth)
+            except Exception as ex:
+                extra["drift_statistics"] = {"error": repr(ex)}
             # ---- e2e: same step from pinned HOST buffers through the public API ---------------------
             host = host_copy(src, torch)
             src = None   # free the resident frame: at c3 (80 GB) it would not fit twice
@@ -277,6 +281,42 @@ def fused_pass_numbers(src, rows, cols, alg_bytes, peak, torch, engine):
         out[name] = {"ms_per_launch": ms, "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
                      "rows_cols_per_s": rows * cols / (ms * 1e-3)}
     return out
+
+
+def drift_numbers(args, src, rows, cols, rank, torch, engine, synth):
+    """drift_detector.statistics(target, source, method_type="all", use_sampling=False) through the public
+    API on two device-resident frames: source K1 + K2, target fused K1+K2 in one read, K3 reduce."""
+    import tempfile
+    import anovos.drift_stability.drift_detector as dd
+    if rows * cols * 8 > 60e9:
+        return {"skipped": "source + target do not fit one GPU at this workload"}
+    tgt = synth.device_frame(rows, cols, seed=43, first_col=rank * cols, shifted=True)
+    d = tempfile.mkdtemp()
+
+    def run():
+        for f in (src, tgt):
+            f._cache = {k: v for k, v in f._cache.items() if isinstance(k, tuple) and k and k[0] == "desc"}
+        return dd.statistics(None, tgt, src, method_type="all", use_sampling=False, source_path=d)
+
+    for _ in range(3):
+        r = run()
+    torch.cuda.synchronize()
+    engine.timer = engine.KernelTimer()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 5))
+    e0.record()
+    for _ in range(steps):
+        r = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    kt = engine.timer.totals()
+    engine.timer = None
+    flagged = int(r.toPandas()["flagged"].sum())
+    del tgt
+    return {"ms_per_call": ms, "rows_cols_per_s": rows * cols / (ms * 1e-3), "flagged_columns": flagged,
+            "kernels_ms_per_call": {k: v["ms"] / steps for k, v in sorted(kt.items())},
+            "note": "rows*cols counts ONE frame; the call reads source twice (K1, K2) and target once (fused)"}
 
 
 def host_copy(src, torch):
