@@ -197,6 +197,39 @@ class ColumnFrame:
     def column(self, name) -> Column:
         return self._cols[name]
 
+    def drop(self, *names) -> "ColumnFrame":
+        """`idf.drop(*cols)`."""
+        names = set(names[0]) if len(names) == 1 and isinstance(names[0], (list, tuple, set)) else set(names)
+        return ColumnFrame(OrderedDict((n, c) for n, c in self._cols.items() if n not in names), self.n_rows)
+
+    def dropna(self, subset=None) -> "ColumnFrame":
+        """`idf.dropna(subset=cols)`: keep the rows whose `subset` columns are all non-null (frame
+        transform on the device with torch indexing: plumbing, not a hot path)."""
+        torch = _lib.require_cuda()
+        subset = list(subset) if subset is not None else self.columns
+        keep = torch.ones(self.n_rows, dtype=torch.bool, device="cuda")
+        rows = torch.arange(self.n_rows, device="cuda")
+        for n in subset:
+            d, v = self._cols[n].device()
+            if v is not None:
+                keep &= ((v[rows >> 5] >> (rows & 31).to(torch.int32)) & 1).bool()
+        idx = torch.nonzero(keep).flatten()
+        m = int(idx.numel())
+        out = OrderedDict()
+        for n, c in self._cols.items():
+            if c.kind == "other":
+                out[n] = Column(n, c.sdtype, m)
+                continue
+            d, v = c.device()
+            nv = None
+            if v is not None:
+                bits = ((v[idx >> 5] >> (idx & 31).to(torch.int32)) & 1).to(torch.uint8).cpu().numpy().astype(bool)
+                if not bits.all():
+                    nv = torch.from_numpy(_pack_validity(bits)).cuda()
+            out[n] = Column(n, c.sdtype, m, dev=d.index_select(0, idx), dev_valid=nv, anv_dtype=c.anv_dtype,
+                            dictionary=c.dictionary)
+        return ColumnFrame(out, m)
+
     def __contains__(self, name):
         return name in self._cols
 

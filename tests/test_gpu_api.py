@@ -417,3 +417,38 @@ class ResultLike:
 
     def toPandas(self):
         return self.df
+
+
+# ---- N2: quality_checker consumers (data_analyzer/test_quality_checker.py:252-524) ---------------------------
+
+def test_quality_checker_consumers():
+    import anovos.data_analyzer.quality_checker as qc
+    t3 = O.table_from_rows([("27520a", 51, 9000, "HS-grad"), ("10a", 42, 7000, "Postgrad"), ("11a", 35, None, "graduate"),
+                            ("1100b", 23, 6000, "matric")], ["ifa", "age", "income", "education"])
+    odf, pr = qc.IDness_detection(None, t3, drop_cols=["ifa"], treatment=False, treatment_threshold=1.0)     # :278-307
+    assert len(odf.columns) == 4
+    e = _rec(pr, "education")
+    assert e["unique_values"] == 4 and e["IDness"] == 1.0 and e["flagged"] == 1
+    odf, pr = qc.IDness_detection(None, t3, drop_cols=["ifa"], treatment=True, treatment_threshold=1.0)      # :309-338
+    assert len(odf.columns) == 1 and _rec(pr, "education")["treated"] == 1
+    t4 = O.table_from_rows([("27520a", 51, 9000, "HS-grad"), ("10a", 42, 7000, "HS-grad"), ("11a", 35, None, "HS-grad"),
+                            ("11d", 45, 9500, "HS-grad"), ("1100b", 23, 6000, "matric")], ["ifa", "age", "income", "education"])
+    odf, pr = qc.biasedness_detection(None, t4, treatment=False, treatment_threshold=0.8)                    # :366-392
+    e = _rec(pr, "education")
+    assert len(odf.columns) == 4 and e["mode"] == "HS-grad" and e["mode_pct"] == 0.8 and e["flagged"] == 1
+    odf, pr = qc.biasedness_detection(None, t4, treatment=True, treatment_threshold=0.8)                     # :394-420
+    e = _rec(pr, "education")
+    assert len(odf.columns) == 3 and e["mode"] == "HS-grad" and e["mode_pct"] == 0.8 and e["treated"] == 1
+    t6 = O.table_from_rows([("27520a", 51, 9000, "HS-grad"), ("10a", 42, 7000, "Postgrad"), ("11a", 35, None, None),
+                            ("1100b", 23, 6000, "HS-grad")], ["ifa", "age", "income", "education"])
+    odf, pr = qc.nullColumns_detection(None, t6, treatment=True)                                             # :492-524
+    assert len(odf.columns) == 4 and odf.count() == 3
+    assert _rec(pr, "education")["missing_count"] == 1 and _rec(pr, "education")["missing_pct"] == 0.25
+    assert _rec(pr, "income")["missing_count"] == 1 and _rec(pr, "income")["missing_pct"] == 0.25
+    odf, pr = qc.nullColumns_detection(None, t6, treatment=True, treatment_method="column_removal",
+                                       treatment_configs={"treatment_threshold": 0.2})
+    assert odf.columns == ["ifa", "age"]
+    with pytest.raises(TypeError):
+        qc.nullColumns_detection(None, t6, treatment=True, treatment_method="column_removal")
+    with pytest.raises(TypeError):
+        qc.IDness_detection(None, t3, treatment="maybe")
