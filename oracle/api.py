@@ -705,3 +705,90 @@ def stability_index_computation(tables, list_of_cols="all", drop_cols=[], metric
         df.sort_values("idx", kind="stable").to_csv(os.path.join(appended_metric_path, "part-00000.csv"), index=False)
     return pd.DataFrame(rows, columns=["attribute", "type", "mean_stddev", "mean_cv", "stddev_cv", "kurtosis_cv", "mean_si",
                                        "stddev_si", "kurtosis_si", "stability_index", "flagged"])
+
+
+# ---------------------------------------------------------------------------
+# N3: IV_calculation / IG_calculation (data_analyzer/association_evaluator.py:253-586)
+# ---------------------------------------------------------------------------
+
+
+def _label_classes(table, label_col, event_label):
+    vals, valid = S.column_values(table, label_col)
+    if vals.dtype == object:
+        ev = valid & (vals.astype(str) == str(event_label))
+    else:
+        ev = valid & (vals.astype(np.float64) == float(event_label))
+    return ev, valid & ~ev          # event rows, non-event rows (label null -> neither)
+
+
+def _encoded_groups(table, col, encoding_configs):
+    """-> (group key per row [object array, None = null group])."""
+    p = ColumnProfile(table, col)
+    if p.is_num and encoding_configs:
+        if encoding_configs.get("monotonicity_check", 0) == 1:
+            raise NotImplementedError("monotonic_binning is not restated")
+        bs, bm = encoding_configs["bin_size"], encoding_configs["bin_method"]
+        if p.n == 0:
+            return np.array([None] * p.N, dtype=object)
+        cut = S.equal_frequency_cutoffs(p.sorted64, bs) if bm == "equal_frequency" else \
+            S.equal_range_cutoffs(*p.minmax(), bs)
+        ids = S.assign_bins(p.values.astype(np.float64), p.valid, cut, bs)
+        return np.array([int(k) if ok else None for k, ok in zip(ids, p.valid)], dtype=object)
+    return np.array([(v if ok else None) for v, ok in zip(p.values.tolist(), p.valid)], dtype=object)
+
+
+def _iv_ig_cols(table, list_of_cols, drop_cols, label_col, event_label):
+    if label_col not in table.column_names:
+        raise TypeError("Invalid input for Label Column")
+    if isinstance(list_of_cols, str) and list_of_cols == "all":
+        num, cat, _ = S.segregate(table)
+        list_of_cols = num + cat
+    cols = _dedupe(_split(list_of_cols), _split(drop_cols) + [label_col])
+    if any(c not in table.column_names for c in cols) or not cols:
+        raise TypeError("Invalid input for Column(s)")
+    ev, nev = _label_classes(table, label_col, event_label)
+    if ev.sum() == 0:
+        raise TypeError("Invalid input for Event Label Value")
+    return cols, ev, nev
+
+
+_DEFAULT_ENC = {"bin_method": "equal_frequency", "bin_size": 10, "monotonicity_check": 0}
+
+
+def IV_calculation(table, list_of_cols="all", drop_cols=[], label_col="label", event_label=1, encoding_configs=_DEFAULT_ENC):
+    """association_evaluator.py:253-424."""
+    cols, ev, nev = _iv_ig_cols(table, list_of_cols, drop_cols, label_col, event_label)
+    rows = []
+    for c in cols:
+        keys = _encoded_groups(table, c, encoding_configs)
+        t0, t1 = float(nev.sum()), float(ev.sum())
+        iv = 0.0
+        for g in set(keys.tolist()):
+            m = np.array([k == g for k in keys.tolist()]) if g is not None else np.array([k is None for k in keys.tolist()])
+            l0, l1 = float((m & nev).sum()), float((m & ev).sum())
+            ne, e = l0 / t0, l1 / t1
+            woe = math.log(ne / e) if (ne != 0 and e != 0) else math.log(((l0 + 0.5) / t0) / ((l1 + 0.5) / t1))
+            iv += woe * (ne - e)
+        rows.append([c, iv])
+    return pd.DataFrame(rows, columns=["attribute", "iv"])
+
+
+def IG_calculation(table, list_of_cols="all", drop_cols=[], label_col="label", event_label=1, encoding_configs=_DEFAULT_ENC):
+    """association_evaluator.py:427-586.  log2(0) is NULL in Spark SQL, so a segment whose event_pct is 0 or 1
+    contributes nothing to entropy_sum."""
+    cols, ev, nev = _iv_ig_cols(table, list_of_cols, drop_cols, label_col, event_label)
+    n = table.num_rows
+    te = ev.sum() / n
+    total_entropy = -(te * math.log2(te) + (1 - te) * math.log2(1 - te))
+    rows = []
+    for c in cols:
+        keys = _encoded_groups(table, c, encoding_configs)
+        s = 0.0
+        for g in set(keys.tolist()):
+            m = np.array([k == g for k in keys.tolist()]) if g is not None else np.array([k is None for k in keys.tolist()])
+            tc, ec = float(m.sum()), float((m & ev).sum())     # count(label) after the when/otherwise recode: every row
+            p = ec / tc
+            if 0 < p < 1:
+                s += -(tc / n) * (p * math.log2(p) + (1 - p) * math.log2(1 - p))
+        rows.append([c, total_entropy - s])
+    return pd.DataFrame(rows, columns=["attribute", "ig"])

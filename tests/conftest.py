@@ -28,6 +28,12 @@ def income_source():
 
 
 @pytest.fixture(scope="session")
+def income_part0():
+    import pyarrow.parquet as pq
+    return pq.read_table(os.path.join(GOLDEN, "income_part0.parquet"))
+
+
+@pytest.fixture(scope="session")
 def income_part1():
     import pyarrow.parquet as pq
     return pq.read_table(os.path.join(GOLDEN, "income_part1.parquet"))

@@ -10,6 +10,7 @@ reference stores in its notebooks, plus the input datasets they were computed on
                           notebooks do), typed like Spark's CSV inferSchema
   income_source.parquet   examples/data/income_dataset/source/sample1.csv (drift source)
   income_part1.parquet    data/test_dataset/part-00001-*.snappy.parquet (test_transformers.py:22)
+  income_part0.parquet    data/test_dataset/part-00000-*.snappy.parquet (test_association_evaluator.py:17)
   stability.parquet       examples/data/income_dataset/stability_index/{0..11} stacked, column `_ds` = dataset id
   notebook_stats.json     stored outputs of examples/notebooks/data_analyzer__stats_generator.ipynb
   notebook_drift.json     stored outputs of examples/notebooks/drift_stability.ipynb
@@ -98,6 +99,9 @@ def main():
     shutil.copyfile(REF + "/data/test_dataset/part-00001-3eb0f7bb-05c2-46ec-8913-23ba231d2734-c000.snappy.parquet",
                     OUT + "/income_part1.parquet")
     os.chmod(OUT + "/income_part1.parquet", 0o644)
+    shutil.copyfile(REF + "/data/test_dataset/part-00000-3eb0f7bb-05c2-46ec-8913-23ba231d2734-c000.snappy.parquet",
+                    OUT + "/income_part0.parquet")   # test_association_evaluator.py:17, test_quality_checker.py:16
+    os.chmod(OUT + "/income_part0.parquet", 0o644)
     parts = []
     for ds in range(12):
         d = REF + "/examples/data/income_dataset/stability_index/%d" % ds

@@ -452,3 +452,29 @@ def test_quality_checker_consumers():
         qc.nullColumns_detection(None, t6, treatment=True, treatment_method="column_removal")
     with pytest.raises(TypeError):
         qc.IDness_detection(None, t3, treatment="maybe")
+
+
+# ---- N3: IV / IG (data_analyzer/test_association_evaluator.py:25-240) ------------------------------------------
+
+def test_iv_ig(income_part0):
+    import anovos.data_analyzer.association_evaluator as ae
+    from test_oracle_golden import check_iv_ig, label_table
+    t = label_table(income_part0)
+    iv, ig = ae.IV_calculation(None, t, drop_cols=["ifa"]).toPandas(), ae.IG_calculation(None, t, drop_cols=["ifa"]).toPandas()
+    check_iv_ig(iv, ig)
+    oiv, oig = O.IV_calculation(t, drop_cols=["ifa"]), O.IG_calculation(t, drop_cols=["ifa"])
+    assert np.allclose(iv["iv"].values, oiv["iv"].values, rtol=1e-12, atol=1e-14)      # same counts -> same floats
+    assert np.allclose(ig["ig"].values, oig["ig"].values, rtol=1e-12, atol=1e-14)
+    er = ae.IV_calculation(None, t, list_of_cols=["age", "fnlwgt"], encoding_configs={"bin_method": "equal_range", "bin_size": 7,
+                                                                                      "monotonicity_check": 0}).toPandas()
+    eo = O.IV_calculation(t, list_of_cols=["age", "fnlwgt"], encoding_configs={"bin_method": "equal_range", "bin_size": 7,
+                                                                               "monotonicity_check": 0})
+    assert np.allclose(er["iv"].values, eo["iv"].values, rtol=1e-12)
+    with pytest.raises(TypeError):
+        ae.IV_calculation(None, t, label_col="nope")
+    with pytest.raises(TypeError):
+        ae.IG_calculation(None, t, event_label=7)
+    # a string label works too
+    ts = income_part0
+    a = ae.IV_calculation(None, ts, list_of_cols=["sex", "age"], label_col="income", event_label=">50K").toPandas()
+    assert abs(a.set_index("attribute").loc["sex", "iv"] - 0.3111) < 5e-5

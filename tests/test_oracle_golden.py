@@ -361,3 +361,38 @@ def check_stability_notebook(fn, nb_drift, tmp_path):
 
 def test_nb_stability_index(nb_drift, tmp_path):
     check_stability_notebook(lambda tables, **kw: O.stability_index_computation(tables, **kw), nb_drift, tmp_path)
+
+
+# ---- N3: data_analyzer/test_association_evaluator.py:25-240 (IV / IG on the income parquet part-00000) ----------
+
+IV_PINS = {"relationship": 1.6208, "marital-status": 1.3929, "occupation": 0.7686, "education": 0.7525, "education-num": 0.7095,
+           "capital-gain": 0.3184, "sex": 0.3111, "workclass": 0.1686}
+IG_PINS = {"relationship": 0.1702, "marital-status": 0.1608, "occupation": 0.0916, "education": 0.0938, "education-num": 0.0887,
+           "capital-gain": 0.0434, "sex": 0.0379, "workclass": 0.0223}
+# these two reference pins come out of approxQuantile(0.01) cutoffs (GK sketch): exact-rank cutoffs land within 10 %
+APPROX_PINS = {"age": (1.1891, 0.0944), "hours-per-week": (0.4441, 0.0549)}
+
+
+def label_table(income_part0):
+    inc = np.array(income_part0.column("income").to_pylist(), dtype=object)
+    return income_part0.drop_columns(["income"]).append_column("label", pa.array(np.where(inc == "<=50K", 0.0, 1.0)))
+
+
+def check_iv_ig(iv, ig):
+    iv, ig = frame_by_attr(iv), frame_by_attr(ig)
+    assert len(iv) == 15 and len(ig) == 15
+    for a, v in IV_PINS.items():
+        assert round(iv[a]["iv"], 4) == v, (a, iv[a]["iv"], v)
+    for a, v in IG_PINS.items():
+        assert round(ig[a]["ig"], 4) == v, (a, ig[a]["ig"], v)
+    for a, (v1, v2) in APPROX_PINS.items():
+        assert abs(iv[a]["iv"] - v1) < 0.1 * v1 and abs(ig[a]["ig"] - v2) < 0.1 * v2
+
+
+def test_iv_ig_known_answers(income_part0):
+    t = label_table(income_part0)
+    check_iv_ig(O.IV_calculation(t, drop_cols=["ifa"]), O.IG_calculation(t, drop_cols=["ifa"]))
+    with pytest.raises(TypeError):
+        O.IV_calculation(t, label_col="nope")
+    with pytest.raises(TypeError):
+        O.IV_calculation(t, event_label=7)
