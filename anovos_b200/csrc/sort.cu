@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
     const bool ok = (w0 + r * 32 + lane) < nt;
     const uint32_t act = __ballot_sync(ANV_FULL, ok);
     const uint32_t d = digit_of(key[r], P.pass);
+#ifdef ANV_SORT_MATCH
+    uint32_t m = __match_any_sync(ANV_FULL, ok ? d : 0xFFFFFFFFu) & act;
+#else
     uint32_t m = act;
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
       const uint32_t bal = __ballot_sync(ANV_FULL, bit);
       m &= bit ? bal : ~bal;
     }
+#endif
     peers[r] = ok ? m : 0u;
   }
   __syncthreads();

@@ -26,6 +26,34 @@ def frames_to_matrix(frames):
     return np.ascontiguousarray(np.concatenate(cols, axis=1)), names
 
 
+class PendingGather:
+    """Handle of an asynchronous summary all_gather: `.result()` waits and returns the per-rank matrices."""
+
+    def __init__(self, work, out, n_rows):
+        self.work, self.out, self.n_rows = work, out, n_rows
+
+    def result(self):
+        self.work.wait()
+        return [o[:n].cpu().numpy() for o, n in zip(self.out, self.n_rows)]
+
+
+def gather_summaries_async(matrix: np.ndarray, n_max: int, device=None) -> PendingGather:
+    """Non-blocking all_gather of fixed-shape [n_max, n_fields] padded summaries (every rank passes the same
+    n_max, e.g. ceil(C / world)): ranks do not wait for each other inside a step, only when the result is
+    consumed.  Rows beyond a rank's own column count are NaN."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    t = torch.from_numpy(np.ascontiguousarray(matrix, dtype=np.float64))
+    pad = torch.full((n_max, t.shape[1]), float("nan"), dtype=torch.float64)
+    pad[:t.shape[0]] = t
+    if device is not None:
+        pad = pad.to(device)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    work = dist.all_gather(out, pad, async_op=True)
+    return PendingGather(work, out, [n_max] * world)
+
+
 def gather_summaries(matrix: np.ndarray, device=None):
     """all_gather of each rank's [n_local_cols, n_fields] summary matrix -> list over ranks.
     Ranks may own different numbers of columns: matrices are padded to the largest."""

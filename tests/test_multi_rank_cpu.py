@@ -27,6 +27,9 @@ def _worker(rank, world, port, ret):
     f2 = pd.DataFrame({"attribute": mine, "skewness": [10.0 + float(n[1:]) for n in mine]})
     m, fields = parallel.frames_to_matrix([f1, f2])
     parts = parallel.gather_summaries(m)
+    h = parallel.gather_summaries_async(m, 4)                 # fixed-shape, non-blocking variant
+    parts2 = [p[~np.isnan(p[:, 0])] for p in h.result()]
+    assert all(np.array_equal(a, b) for a, b in zip(parts, parts2))
     dist.destroy_process_group()
     ret[rank] = (mine, fields, [p.tolist() for p in parts])
 
