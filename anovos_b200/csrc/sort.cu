@@ -175,6 +175,21 @@ __global__ void __launch_bounds__(ANV_BLOCK) pack_kernel(const SortParams<K> P) 
   }
 }
 
+// Lanes of `act` holding the same 8-bit digit: per bit one predicate test, one ballot and one predicated
+// AND / AND-NOT (4 SASS instructions per bit; the C++ form compiles to 6).
+#define ANV_PEER_BIT(B)                                                                              \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, bal;\n\tand.b32 t, %1, " #B ";\n\tsetp.ne.u32 p, t, 0;\n\t"     \
+               "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t@p and.b32 %0, %0, bal;\n\t"                 \
+               "@!p lop3.b32 %0, %0, bal, 0, 0x30;\n\t}"                                                 \
+               : "+r"(m) : "r"(d))
+__device__ __forceinline__ uint32_t peers8(uint32_t d, uint32_t act) {
+  uint32_t m = act;
+  ANV_PEER_BIT(1); ANV_PEER_BIT(2); ANV_PEER_BIT(4); ANV_PEER_BIT(8);
+  ANV_PEER_BIT(16); ANV_PEER_BIT(32); ANV_PEER_BIT(64); ANV_PEER_BIT(128);
+  return m;
+}
+#undef ANV_PEER_BIT
+
 template <typename K> __device__ __forceinline__ uint32_t digit_of(K k, int pass) {
   return (uint32_t)(k >> (pass * 8)) & 0xFFu;
 }
@@ -211,9 +226,7 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_hist_kernel(const SortParams<K
     for (int i = nvec * KV + tid; i < nt; i += ANV_BLOCK) atomicAdd(&h[digit_of(keys[i], P.pass)], 1u);
   }
   __syncthreads();
-  const uint32_t v = h[tid];
-  P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile] = v;
-  if (v) atomicAdd(&P.digit_total[(size_t)c * 256 + tid], (unsigned long long)v);
+  P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile] = h[tid];
 }
 
 // ---- pass step 2: per-column exclusive scan of [256][n_tiles] + skip decision ----------------------
@@ -227,48 +240,51 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortParams<K> P) 
   if (tid == 0) { s_skip = 0; s_carry = 0; }
   __syncthreads();
   const unsigned long long n = S.n_valid;
-  if (tid < 256) {
-    const unsigned long long t = P.digit_total[(size_t)c * 256 + tid];
-    if (n == 0 || t == n) s_skip = 1;          // (benign race: every writer writes 1)
-    P.digit_total[(size_t)c * 256 + tid] = 0;  // ready for the next pass
+  uint32_t* a = P.tile_hist + (size_t)c * 256 * P.n_tiles;
+  const int64_t total = (int64_t)256 * P.n_tiles;
+  if (n > 0) {
+    for (int64_t base = 0; base < total; base += 1024 * 4) {
+      uint32_t v[4], run = 0;
+      const int64_t i0 = base + (int64_t)tid * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < total) ? a[i0 + k] : 0u; run += v[k]; }
+      uint32_t inc = run;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o);
+        if ((tid & 31) >= o) inc += t;
+      }
+      if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+      __syncthreads();
+      if (tid < 32) {
+        uint32_t w = wsum[tid], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(ANV_FULL, wi, o);
+          if (tid >= o) wi += t;
+        }
+        wsum[tid] = wi - w;  // exclusive
+      }
+      __syncthreads();
+      uint32_t ex = s_carry + wsum[tid >> 5] + inc - run;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { if (i0 + k < total) a[i0 + k] = ex; ex += v[k]; }
+      __syncthreads();
+      if (tid == 1023) s_carry = ex;
+      __syncthreads();
+    }
   }
+  // a digit whose total is n (its segment spans the whole prefix range) makes the pass a no-op: skip the scatter
+  if (tid < 256 && n > 0) {
+    const unsigned long long lo = a[(size_t)tid * P.n_tiles];
+    const unsigned long long hi = (tid == 255) ? n : a[(size_t)(tid + 1) * P.n_tiles];
+    if (hi - lo == n) s_skip = 1;  // (benign race: every writer writes 1)
+  }
+  if (tid == 0 && n == 0) s_skip = 1;
   __syncthreads();
-  const int skip = s_skip;
   if (tid == 0) {
+    const int skip = s_skip;
     S.src[P.pass] = S.cur;
     S.skip[P.pass] = skip;
     if (!skip) S.cur ^= 1;
-  }
-  if (skip) return;
-  uint32_t* a = P.tile_hist + (size_t)c * 256 * P.n_tiles;
-  const int64_t total = (int64_t)256 * P.n_tiles;
-  for (int64_t base = 0; base < total; base += 1024 * 4) {
-    uint32_t v[4], run = 0;
-    const int64_t i0 = base + (int64_t)tid * 4;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < total) ? a[i0 + k] : 0u; run += v[k]; }
-    uint32_t inc = run;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o);
-      if ((tid & 31) >= o) inc += t;
-    }
-    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
-    __syncthreads();
-    if (tid < 32) {
-      uint32_t w = wsum[tid], wi = w;
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(ANV_FULL, wi, o);
-        if (tid >= o) wi += t;
-      }
-      wsum[tid] = wi - w;  // exclusive
-    }
-    __syncthreads();
-    uint32_t ex = s_carry + wsum[tid >> 5] + inc - run;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { if (i0 + k < total) a[i0 + k] = ex; ex += v[k]; }
-    __syncthreads();
-    if (tid == 1023) s_carry = ex;
-    __syncthreads();
   }
 }
 
@@ -312,17 +328,7 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
     const bool ok = (w0 + r * 32 + lane) < nt;
     const uint32_t act = __ballot_sync(ANV_FULL, ok);
     const uint32_t d = digit_of(key[r], P.pass);
-#ifdef ANV_SORT_MATCH
-    uint32_t m = __match_any_sync(ANV_FULL, ok ? d : 0xFFFFFFFFu) & act;
-#else
-    uint32_t m = act;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const bool bit = (d >> b) & 1u;
-      const uint32_t bal = __ballot_sync(ANV_FULL, bit);
-      m &= bit ? bal : ~bal;
-    }
-#endif
+    const uint32_t m = peers8(d, act);
     peers[r] = ok ? m : 0u;
   }
   __syncthreads();
@@ -378,57 +384,6 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
   }
 }
 
-// ---- run summary of the sorted keys --------------------------------------------------------------
-template <typename K>
-__global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K> P) {
-  const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-  const ColState& S = P.state[c];
-  const int64_t n = (int64_t)S.n_valid;
-  const int64_t t0 = (int64_t)tile * SORT_TILE;
-  TileSummary<K>& out = P.summ[(size_t)c * P.n_tiles + tile];
-  if (t0 >= n) { if (tid == 0) out.n = 0; return; }
-  const int nt = (int)min((int64_t)SORT_TILE, n - t0);
-  const K* __restrict__ keys = (S.cur ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride + t0;
-  __shared__ K sk[SORT_TILE];
-  __shared__ unsigned long long s_best;
-  __shared__ uint32_t s_heads, s_prefix, s_suffix;
-  for (int i = tid; i < nt; i += ANV_BLOCK) sk[i] = keys[i];
-  if (tid == 0) { s_best = 0; s_heads = 0; s_prefix = 0; s_suffix = 0; }
-  __syncthreads();
-  uint32_t heads = 0;
-  unsigned long long best = 0;
-  for (int i = tid; i < nt; i += ANV_BLOCK) {
-    if (i > 0 && sk[i] == sk[i - 1]) continue;  // not a run head
-    heads += i > 0;
-    int e = i + 1;                              // end (exclusive) of the run starting at i
-    if (e < nt && sk[e] == sk[i]) {             // upper bound by binary search (keys are sorted)
-      int lo = e, hi = nt;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] == sk[i]) lo = mid + 1; else hi = mid; }
-      e = lo;
-    }
-    const uint32_t len = (uint32_t)(e - i);
-    if (i == 0) s_prefix = len;
-    if (e == nt) s_suffix = len;
-    if (i > 0 && e < nt) {
-      const unsigned long long v = ((unsigned long long)len << 32) | (uint32_t)(SORT_TILE - i);  // max len, then smallest i
-      best = v > best ? v : best;
-    }
-  }
-  if (heads) atomicAdd(&s_heads, heads);
-  if (best) atomicMax(&s_best, best);
-  __syncthreads();
-  if (tid == 0) {
-    out.n = nt;
-    out.first_key = sk[0];
-    out.last_key = sk[nt - 1];
-    out.prefix_len = s_prefix;
-    out.suffix_len = s_suffix;
-    out.heads_inside = s_heads;
-    out.best_len = (uint32_t)(s_best >> 32);
-    out.best_key = s_best ? sk[SORT_TILE - (int)(uint32_t)s_best] : (K)0;
-  }
-}
-
 // Associative combine of two ADJACENT run summaries (left, right) of sorted keys.
 template <typename K> __device__ __forceinline__ void best_of(K& bk, uint32_t& bl, K k, uint32_t len) {
   if (len > bl) { bl = len; bk = k; }  // candidates arrive in ascending key order: strict > keeps the smallest key
@@ -468,6 +423,73 @@ template <typename K> __device__ __forceinline__ TileSummary<K> shfl_down_summar
   r.suffix_len = __shfl_down_sync(ANV_FULL, s.suffix_len, d); r.best_len = __shfl_down_sync(ANV_FULL, s.best_len, d);
   r.heads_inside = __shfl_down_sync(ANV_FULL, s.heads_inside, d);
   return r;
+}
+
+// ---- run summary of the sorted keys --------------------------------------------------------------
+// Each thread summarises 16 CONSECUTIVE sorted keys in registers (blocked 128-bit loads), the 256
+// thread summaries are folded with the associative `combine` (shuffle tree per warp, then 8 warps
+// sequentially): no shared-memory tile, no binary search, ~25 instructions per key.
+template <typename K>
+__global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K> P) {
+  const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const ColState& S = P.state[c];
+  const int64_t n = (int64_t)S.n_valid;
+  const int64_t t0 = (int64_t)tile * SORT_TILE;
+  TileSummary<K>& out = P.summ[(size_t)c * P.n_tiles + tile];
+  if (t0 >= n) { if (tid == 0) out.n = 0; return; }
+  const int nt = (int)min((int64_t)SORT_TILE, n - t0);
+  const K* __restrict__ keys = (S.cur ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride + t0;
+  constexpr int PER = SORT_TILE / ANV_BLOCK;  // 16
+  constexpr int KV = 16 / sizeof(K);
+  const int m = max(0, min(PER, nt - tid * PER));
+  K k[PER];
+  if (m == PER) {
+    const uint4* p = reinterpret_cast<const uint4*>(keys + tid * PER);
+#pragma unroll
+    for (int v = 0; v < PER / KV; ++v) {
+      const uint4 q = __ldg(p + v);
+      if (sizeof(K) == 4) { k[v * 4] = (K)q.x; k[v * 4 + 1] = (K)q.y; k[v * 4 + 2] = (K)q.z; k[v * 4 + 3] = (K)q.w; }
+      else { k[v * KV] = (K)(((uint64_t)q.y << 32) | q.x); k[v * KV + (KV > 1 ? 1 : 0)] = (K)(((uint64_t)q.w << 32) | q.z); }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) k[j] = (j < m) ? keys[tid * PER + j] : (K)0;
+  }
+  TileSummary<K> s;
+  s.n = m; s.first_key = k[0]; s.best_key = 0; s.best_len = 0; s.heads_inside = 0; s.prefix_len = 0;
+  uint32_t run = 1;
+  K last = k[0];
+#pragma unroll
+  for (int j = 1; j < PER; ++j) {
+    if (j < m) {
+      if (k[j] == k[j - 1]) {
+        ++run;
+      } else {
+        if (s.heads_inside == 0) s.prefix_len = run;
+        else if (run > s.best_len) { s.best_len = run; s.best_key = k[j - 1]; }
+        ++s.heads_inside;
+        run = 1;
+      }
+      last = k[j];
+    }
+  }
+  s.last_key = last;
+  s.suffix_len = m ? run : 0;
+  if (s.heads_inside == 0) s.prefix_len = m;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const TileSummary<K> right = shfl_down_summary(s, o);
+    if ((lane & (2 * o - 1)) == 0) s = combine(s, right);
+  }
+  __shared__ TileSummary<K> ws[ANV_WARPS];
+  if (lane == 0) ws[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    TileSummary<K> acc = ws[0];
+#pragma unroll
+    for (int w = 1; w < ANV_WARPS; ++w) acc = combine(acc, ws[w]);
+    out = acc;
+  }
 }
 
 // One warp per column: 32 tile summaries per step are combined with an order-preserving
@@ -557,7 +579,6 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   P.digit_total = reinterpret_cast<unsigned long long*>(w + L.digit_total);
   P.summ = reinterpret_cast<TileSummary<K>*>(w + L.summ);
   ANV_CUDA(cudaMemsetAsync(P.state, 0, (size_t)n_cols * sizeof(ColState), st));
-  ANV_CUDA(cudaMemsetAsync(P.digit_total, 0, (size_t)n_cols * 256 * 8, st));
   if (n_rows > 0) {
     dim3 grid(P.n_tiles, n_cols);
     pack_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
