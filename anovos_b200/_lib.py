@@ -54,12 +54,19 @@ _SIGNATURES = {
     "anv_drift_reduce": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, _I, _L, _L, _P, _P]),
     "anv_select_workspace_bytes": (_SZ, [_I, _I]),
     "anv_select_ranks": (C.c_int, [_P, _I, _L, _P, _I, _I, _P, _P, _SZ, _P]),
+    "anv_select_passes": (C.c_int, [_I]),
+    "anv_select_begin": (C.c_int, [_I, _I, _P, _SZ, _P]),
+    "anv_select_hist_region": (C.c_int, [_I, _I, _I, _P, _P]),
+    "anv_select_accumulate": (C.c_int, [_P, _I, _L, _I, _I, _I, _P, _SZ, _P]),
+    "anv_select_advance": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "anv_hll_registers": (C.c_int, [_P, _I, _L, _I, _P, _P]),
     "anv_xxh64_utf8": (C.c_int, [_P, _P, _L, _P]),
     "anv_mode_distinct_workspace_bytes": (_SZ, [_I, _L, _I]),
     "anv_mode_distinct": (C.c_int, [_P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "anv_synth_f32": (C.c_int, [_P, _P, _L, C.c_uint64, C.c_uint32, _I, C.c_float, C.c_float, C.c_float, _P]),
     "anv_synth_codes": (C.c_int, [_P, _P, _L, C.c_uint64, C.c_uint32, _I, C.c_float, C.c_float, _P]),
+    "anv_synth_f32_rows": (C.c_int, [_P, _P, _L, _L, C.c_uint64, C.c_uint32, _I, C.c_float, C.c_float, C.c_float, _P]),
+    "anv_synth_codes_rows": (C.c_int, [_P, _P, _L, _L, C.c_uint64, C.c_uint32, _I, C.c_float, C.c_float, _P]),
 }
 
 

@@ -314,51 +314,127 @@ extern "C" size_t anv_select_workspace_bytes(int n_cols, int n_ranks) {
          (size_t)n_cols * n_ranks * (1 << SEL_BITS) * 8 + 256;
 }
 
-extern "C" int anv_select_ranks(const anv_column_t* cols, int n_cols, int64_t n_rows, const int64_t* ranks, int n_ranks,
-                                int key_bits, double* out, void* workspace, size_t workspace_bytes, void* stream) {
-  if (n_cols < 0 || n_rows < 0 || n_ranks < 1 || n_ranks > SEL_MAX_RANKS || (key_bits != 32 && key_bits != 64)) {
-    set_error("anv_select_ranks: bad arguments (1 <= n_ranks <= %d, key_bits 32|64)", SEL_MAX_RANKS);
+namespace {
+struct SelLayout {
+  SelState* state;
+  unsigned long long* hist0;
+  unsigned long long* histN;
+  size_t h0, hN;
+};
+SelLayout sel_layout(void* workspace, int n_cols, int n_ranks) {
+  char* w = reinterpret_cast<char*>(workspace);
+  SelLayout L;
+  L.state = reinterpret_cast<SelState*>(w);
+  const size_t off = ((size_t)n_cols * sizeof(SelState) + 127) & ~(size_t)127;
+  L.hist0 = reinterpret_cast<unsigned long long*>(w + off);
+  L.h0 = (size_t)n_cols * (1 << SEL_BITS0) * 8;
+  L.histN = reinterpret_cast<unsigned long long*>(w + off + L.h0);
+  L.hN = (size_t)n_cols * n_ranks * (1 << SEL_BITS) * 8;
+  return L;
+}
+// digit width / position of pass `pass` (12 bits first, then 10 at a time); returns 0 past the last pass
+int sel_pass_geometry(int key_bits, int pass, int* bits, int* shift) {
+  int decided = 0;
+  for (int p = 0; decided < key_bits; ++p) {
+    const int b = p == 0 ? SEL_BITS0 : ((key_bits - decided) < SEL_BITS ? (key_bits - decided) : SEL_BITS);
+    if (p == pass) { *bits = b; *shift = 64 - decided - b; return (decided + b >= key_bits) ? 2 : 1; }
+    decided += b;
+  }
+  return 0;
+}
+int sel_check(const char* who, int n_cols, int n_ranks, int key_bits, const void* ws, size_t ws_bytes) {
+  if (n_cols < 0 || n_ranks < 1 || n_ranks > SEL_MAX_RANKS || (key_bits != 32 && key_bits != 64)) {
+    set_error("%s: bad arguments (1 <= n_ranks <= %d, key_bits 32|64)", who, SEL_MAX_RANKS);
     return ANV_ERR_INVALID;
   }
-  if (n_cols == 0) return ANV_OK;
   if (n_cols > 65535) { set_error("n_cols > 65535"); return ANV_ERR_UNSUPPORTED; }
-  if (!cols || !ranks || !out || !workspace) { set_error("anv_select_ranks: NULL argument"); return ANV_ERR_INVALID; }
-  if (workspace_bytes < anv_select_workspace_bytes(n_cols, n_ranks)) {
-    set_error("anv_select_ranks: workspace too small");
+  if (n_cols && !ws) { set_error("%s: NULL workspace", who); return ANV_ERR_INVALID; }
+  if (n_cols && ws_bytes < anv_select_workspace_bytes(n_cols, n_ranks)) {
+    set_error("%s: workspace too small", who);
     return ANV_ERR_WORKSPACE;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  char* w = reinterpret_cast<char*>(workspace);
-  SelState* state = reinterpret_cast<SelState*>(w);
-  size_t off = ((size_t)n_cols * sizeof(SelState) + 127) & ~(size_t)127;
-  unsigned long long* hist0 = reinterpret_cast<unsigned long long*>(w + off);
-  const size_t h0 = (size_t)n_cols * (1 << SEL_BITS0) * 8;
-  unsigned long long* histN = reinterpret_cast<unsigned long long*>(w + off + h0);
-  const size_t hN = (size_t)n_cols * n_ranks * (1 << SEL_BITS) * 8;
-  ANV_CUDA(cudaMemsetAsync(hist0, 0, h0 + hN, st));
+  return ANV_OK;
+}
+}  // namespace
 
+extern "C" int anv_select_passes(int key_bits) { return key_bits == 32 ? 3 : (key_bits == 64 ? 7 : -1); }
+
+extern "C" int anv_select_begin(int n_cols, int n_ranks, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = sel_check("anv_select_begin", n_cols, n_ranks, 32, workspace, workspace_bytes)) return rc;
+  if (n_cols == 0) return ANV_OK;
+  const SelLayout L = sel_layout(workspace, n_cols, n_ranks);
+  ANV_CUDA(cudaMemsetAsync(L.hist0, 0, L.h0 + L.hN, (cudaStream_t)stream));
+  return ANV_OK;
+}
+
+extern "C" int anv_select_hist_region(int n_cols, int n_ranks, int pass, size_t* offset, size_t* bytes) {
+  if (n_cols < 0 || n_ranks < 1 || n_ranks > SEL_MAX_RANKS || pass < 0 || !offset || !bytes) {
+    set_error("anv_select_hist_region: bad arguments");
+    return ANV_ERR_INVALID;
+  }
+  const size_t off = ((size_t)n_cols * sizeof(SelState) + 127) & ~(size_t)127;
+  const size_t h0 = (size_t)n_cols * (1 << SEL_BITS0) * 8;
+  *offset = pass == 0 ? off : off + h0;
+  *bytes = pass == 0 ? h0 : (size_t)n_cols * n_ranks * (1 << SEL_BITS) * 8;
+  return ANV_OK;
+}
+
+extern "C" int anv_select_accumulate(const anv_column_t* cols, int n_cols, int64_t n_rows, int n_ranks, int key_bits,
+                                     int pass, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = sel_check("anv_select_accumulate", n_cols, n_ranks, key_bits, workspace, workspace_bytes)) return rc;
+  int bits = 0, shift = 0;
+  if (n_rows < 0 || !sel_pass_geometry(key_bits, pass, &bits, &shift)) {
+    set_error("anv_select_accumulate: bad pass %d / n_rows", pass);
+    return ANV_ERR_INVALID;
+  }
+  if (n_cols == 0 || n_rows == 0) return ANV_OK;
+  if (!cols) { set_error("anv_select_accumulate: NULL argument"); return ANV_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const SelLayout L = sel_layout(workspace, n_cols, n_ranks);
   SelParams P{};
-  P.cols = cols; P.n_cols = n_cols; P.n_rows = n_rows; P.n_ranks = n_ranks; P.state = state;
-  P.tile_rows = sel_tile_rows(n_rows > 0 ? n_rows : 1, n_cols);
+  P.cols = cols; P.n_cols = n_cols; P.n_rows = n_rows; P.n_ranks = n_ranks; P.state = L.state;
+  P.tile_rows = sel_tile_rows(n_rows, n_cols);
+  P.pass = pass; P.bits = bits; P.shift = shift;
+  P.hist = pass == 0 ? L.hist0 : L.histN;
   dim3 grid((unsigned)((n_rows + P.tile_rows - 1) / P.tile_rows), (unsigned)n_cols);
-  const size_t smemN = (size_t)n_ranks * (1 << SEL_BITS) * 4;
-  if (smemN > 40 * 1024)
-    ANV_CUDA(cudaFuncSetAttribute(select_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemN));
-  int decided = 0, pass = 0;
-  while (decided < key_bits) {
-    const int bits = pass == 0 ? SEL_BITS0 : ((key_bits - decided) < SEL_BITS ? (key_bits - decided) : SEL_BITS);
-    P.pass = pass; P.bits = bits; P.shift = 64 - decided - bits;
-    P.hist = pass == 0 ? hist0 : histN;
-    if (n_rows > 0) {
-      if (pass == 0) select_pass_kernel<true><<<grid, ANV_BLOCK, (size_t)(1 << SEL_BITS0) * 4, st>>>(P);
-      else select_pass_kernel<false><<<grid, ANV_BLOCK, smemN, st>>>(P);
-      ANV_CUDA(cudaGetLastError());
-    }
-    decided += bits;
-    const int last = decided >= key_bits;
-    select_scan_kernel<<<n_cols, 256, 0, st>>>(state, P.hist, ranks, n_ranks, pass, bits, last, key_bits, cols, out);
-    ANV_CUDA(cudaGetLastError());
-    ++pass;
+  if (pass == 0) {
+    select_pass_kernel<true><<<grid, ANV_BLOCK, (size_t)(1 << SEL_BITS0) * 4, st>>>(P);
+  } else {
+    const size_t smemN = (size_t)n_ranks * (1 << SEL_BITS) * 4;
+    if (smemN > 40 * 1024)
+      ANV_CUDA(cudaFuncSetAttribute(select_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemN));
+    select_pass_kernel<false><<<grid, ANV_BLOCK, smemN, st>>>(P);
+  }
+  ANV_CUDA(cudaGetLastError());
+  return ANV_OK;
+}
+
+extern "C" int anv_select_advance(const anv_column_t* cols, int n_cols, const int64_t* ranks, int n_ranks, int key_bits,
+                                  int pass, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = sel_check("anv_select_advance", n_cols, n_ranks, key_bits, workspace, workspace_bytes)) return rc;
+  int bits = 0, shift = 0;
+  const int g = sel_pass_geometry(key_bits, pass, &bits, &shift);
+  if (!g) { set_error("anv_select_advance: bad pass %d", pass); return ANV_ERR_INVALID; }
+  if (n_cols == 0) return ANV_OK;
+  if (!cols || !ranks || !out) { set_error("anv_select_advance: NULL argument"); return ANV_ERR_INVALID; }
+  const SelLayout L = sel_layout(workspace, n_cols, n_ranks);
+  select_scan_kernel<<<n_cols, 256, 0, (cudaStream_t)stream>>>(L.state, pass == 0 ? L.hist0 : L.histN, ranks, n_ranks, pass,
+                                                                bits, g == 2, key_bits, cols, out);
+  ANV_CUDA(cudaGetLastError());
+  return ANV_OK;
+}
+
+extern "C" int anv_select_ranks(const anv_column_t* cols, int n_cols, int64_t n_rows, const int64_t* ranks, int n_ranks,
+                                int key_bits, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = sel_check("anv_select_ranks", n_cols, n_ranks, key_bits, workspace, workspace_bytes)) return rc;
+  if (n_rows < 0) { set_error("anv_select_ranks: n_rows < 0"); return ANV_ERR_INVALID; }
+  if (n_cols == 0) return ANV_OK;
+  if (!cols || !ranks || !out) { set_error("anv_select_ranks: NULL argument"); return ANV_ERR_INVALID; }
+  if (int rc = anv_select_begin(n_cols, n_ranks, workspace, workspace_bytes, stream)) return rc;
+  const int n_pass = anv_select_passes(key_bits);
+  for (int pass = 0; pass < n_pass; ++pass) {
+    if (int rc = anv_select_accumulate(cols, n_cols, n_rows, n_ranks, key_bits, pass, workspace, workspace_bytes, stream)) return rc;
+    if (int rc = anv_select_advance(cols, n_cols, ranks, n_ranks, key_bits, pass, out, workspace, workspace_bytes, stream)) return rc;
   }
   return ANV_OK;
 }

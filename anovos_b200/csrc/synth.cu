@@ -27,13 +27,14 @@ __device__ __forceinline__ void normals4(const uint4& r, float (&z)[4]) {
 }
 
 template <typename OutT, typename F>
-__device__ __forceinline__ void synth_loop(OutT* data, uint32_t* validity, int64_t n_rows, uint2 key, float null_rate, F gen) {
+__device__ __forceinline__ void synth_loop(OutT* data, uint32_t* validity, int64_t n_rows, int64_t row0, uint2 key, float null_rate, F gen) {
   const int64_t n4 = (n_rows + 3) / 4;
   const int64_t n4_pad = (n4 + 31) & ~(int64_t)31;  // whole warps so the bitmap words are assembled uniformly
   const uint32_t null_thr = (uint32_t)fminf(null_rate * 4294967296.0f, 4294967040.0f);
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4_pad; j += (int64_t)gridDim.x * blockDim.x) {
     OutT v[4];
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)j, (uint32_t)(j >> 32), 0u, 0u), key);
+    const int64_t g = j + (row0 >> 2);  // counter of the GLOBAL row group: chunk [row0, row0+n) of a frame == the frame's rows
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), 0u, 0u), key);
     gen(r, v);
     const int64_t row = j * 4;
     if (row + 3 < n_rows) {
@@ -42,7 +43,7 @@ __device__ __forceinline__ void synth_loop(OutT* data, uint32_t* validity, int64
       for (int i = 0; i < 4; ++i) if (row + i < n_rows) data[row + i] = v[i];
     }
     if (validity) {
-      const uint4 nr = philox4x32_10(make_uint4((uint32_t)j, (uint32_t)(j >> 32), 1u, 0u), key);
+      const uint4 nr = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), 1u, 0u), key);
       uint32_t nib = 0;
       nib |= (nr.x >= null_thr && row + 0 < n_rows) ? 1u : 0u;
       nib |= (nr.y >= null_thr && row + 1 < n_rows) ? 2u : 0u;
@@ -57,9 +58,9 @@ __device__ __forceinline__ void synth_loop(OutT* data, uint32_t* validity, int64
   }
 }
 
-__global__ void __launch_bounds__(256) synth_f32_kernel(float* data, uint32_t* validity, int64_t n_rows, uint2 key, int family,
+__global__ void __launch_bounds__(256) synth_f32_kernel(float* data, uint32_t* validity, int64_t n_rows, int64_t row0, uint2 key, int family,
                                                         float a, float b, float null_rate) {
-  synth_loop<float>(data, validity, n_rows, key, null_rate, [=](const uint4& r, float (&v)[4]) {
+  synth_loop<float>(data, validity, n_rows, row0, key, null_rate, [=](const uint4& r, float (&v)[4]) {
     if (family == 0) {
       normals4(r, v);
 #pragma unroll
@@ -83,12 +84,12 @@ __global__ void __launch_bounds__(256) synth_f32_kernel(float* data, uint32_t* v
   });
 }
 
-__global__ void __launch_bounds__(256) synth_codes_kernel(int32_t* data, uint32_t* validity, int64_t n_rows, uint2 key,
+__global__ void __launch_bounds__(256) synth_codes_kernel(int32_t* data, uint32_t* validity, int64_t n_rows, int64_t row0, uint2 key,
                                                           int card, float zipf_s, float null_rate) {
   const float one_minus_s = 1.0f - zipf_s;
   const float span = __powf((float)card + 1.0f, one_minus_s) - 1.0f;
   const float inv = 1.0f / one_minus_s;
-  synth_loop<int32_t>(data, validity, n_rows, key, null_rate, [=](const uint4& r, int32_t (&v)[4]) {
+  synth_loop<int32_t>(data, validity, n_rows, row0, key, null_rate, [=](const uint4& r, int32_t (&v)[4]) {
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -106,32 +107,42 @@ static uint2 make_key(uint64_t seed, uint32_t column) {
 
 }  // namespace anv
 
-extern "C" int anv_synth_f32(float* data, uint32_t* validity, int64_t n_rows, uint64_t seed, uint32_t column, int family,
-                             float a, float b, float null_rate, void* stream) {
-  if (!data || n_rows < 0 || family < 0 || family > 3 || ((uintptr_t)data & 15)) {
-    anv::set_error("anv_synth_f32: bad arguments");
+extern "C" int anv_synth_f32_rows(float* data, uint32_t* validity, int64_t n_rows, int64_t row0, uint64_t seed, uint32_t column,
+                                  int family, float a, float b, float null_rate, void* stream) {
+  if (!data || n_rows < 0 || row0 < 0 || (row0 & 31) || family < 0 || family > 3 || ((uintptr_t)data & 15)) {
+    anv::set_error("anv_synth_f32: bad arguments (row0 must be a multiple of 32)");
     return ANV_ERR_INVALID;
   }
   if (n_rows == 0) return ANV_OK;
   const int64_t n4 = (n_rows + 3) / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-  anv::synth_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(data, validity, n_rows, anv::make_key(seed, column), family,
+  anv::synth_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(data, validity, n_rows, row0, anv::make_key(seed, column), family,
                                                                   a, b, null_rate);
   ANV_CUDA(cudaGetLastError());
   return ANV_OK;
 }
 
-extern "C" int anv_synth_codes(int32_t* data, uint32_t* validity, int64_t n_rows, uint64_t seed, uint32_t column,
-                               int cardinality, float zipf_s, float null_rate, void* stream) {
-  if (!data || n_rows < 0 || cardinality < 1 || zipf_s <= 1.0f || ((uintptr_t)data & 15)) {
+extern "C" int anv_synth_f32(float* data, uint32_t* validity, int64_t n_rows, uint64_t seed, uint32_t column, int family,
+                             float a, float b, float null_rate, void* stream) {
+  return anv_synth_f32_rows(data, validity, n_rows, 0, seed, column, family, a, b, null_rate, stream);
+}
+
+extern "C" int anv_synth_codes_rows(int32_t* data, uint32_t* validity, int64_t n_rows, int64_t row0, uint64_t seed,
+                                    uint32_t column, int cardinality, float zipf_s, float null_rate, void* stream) {
+  if (!data || n_rows < 0 || row0 < 0 || (row0 & 31) || cardinality < 1 || zipf_s <= 1.0f || ((uintptr_t)data & 15)) {
     anv::set_error("anv_synth_codes: bad arguments (zipf_s must be > 1)");
     return ANV_ERR_INVALID;
   }
   if (n_rows == 0) return ANV_OK;
   const int64_t n4 = (n_rows + 3) / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-  anv::synth_codes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(data, validity, n_rows, anv::make_key(seed, column),
+  anv::synth_codes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(data, validity, n_rows, row0, anv::make_key(seed, column),
                                                                     cardinality, zipf_s, null_rate);
   ANV_CUDA(cudaGetLastError());
   return ANV_OK;
+}
+
+extern "C" int anv_synth_codes(int32_t* data, uint32_t* validity, int64_t n_rows, uint64_t seed, uint32_t column,
+                               int cardinality, float zipf_s, float null_rate, void* stream) {
+  return anv_synth_codes_rows(data, validity, n_rows, 0, seed, column, cardinality, zipf_s, null_rate, stream);
 }

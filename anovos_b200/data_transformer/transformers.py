@@ -85,6 +85,33 @@ def _labels(cut, n_over_cut):
     return out
 
 
+def _apply_binning(fr: ColumnFrame, cols, cuts, lohi, bin_dtype, output_mode) -> ColumnFrame:
+    """bucket_label (:248-280) for every value of `cols` with the given cutoffs -> new frame."""
+    bm = engine.BinModel(fr, cols, cuts, lohi)
+    ids = engine.bin_assign(fr, bm)                         # [n_cols, n_rows] int32, 0 = null
+    n_over = len(cuts[0]) + 1                               # `len(bin_cutoffs[0]) + 1` quirk (:269)
+    new_cols = OrderedDict((n, fr.column(n)) for n in fr.columns)
+    for i, c in enumerate(cols):
+        src = fr.column(c)
+        _, v = src.device()
+        data = ids[i]
+        if len(cuts[i]) + 1 != n_over:                      # only reachable with a hand-made model
+            data = data.clone()
+            data[data == len(cuts[i]) + 1] = n_over
+        if bin_dtype == "numerical":
+            col = Column(c, "int", fr.n_rows, dev=data, dev_valid=v, anv_dtype=_lib.ANV_I32,
+                         null_count=src.null_count)
+        else:
+            col = Column(c, "string", fr.n_rows, dev=(data - 1).clamp_(min=0), dev_valid=v, anv_dtype=_lib.ANV_I32,
+                         null_count=src.null_count, dictionary=_labels(cuts[i], len(cuts[0])))
+        if output_mode == "replace":
+            new_cols[c] = col
+        else:
+            col.name = c + "_binned"
+            new_cols[c + "_binned"] = col
+    return ColumnFrame(new_cols, fr.n_rows)
+
+
 def attribute_binning(spark, idf, list_of_cols="all", drop_cols=[], method_type="equal_range", bin_size=10,
                       bin_dtype="numerical", pre_existing_model=False, model_path="NA", output_mode="replace",
                       print_impact=False):
@@ -126,29 +153,12 @@ def attribute_binning(spark, idf, list_of_cols="all", drop_cols=[], method_type=
     if not cols:
         return fr
 
-    bm = engine.BinModel(fr, cols, cuts, lohi)
-    ids = engine.bin_assign(fr, bm)                         # [n_cols, n_rows] int32, 0 = null
-    n_over = len(cuts[0]) + 1                               # `len(bin_cutoffs[0]) + 1` quirk (:269)
-    new_cols = OrderedDict((n, fr.column(n)) for n in fr.columns)
-    for i, c in enumerate(cols):
-        src = fr.column(c)
-        _, v = src.device()
-        data = ids[i]
-        if len(cuts[i]) + 1 != n_over:                      # only reachable with a hand-made model
-            data = data.clone()
-            data[data == len(cuts[i]) + 1] = n_over
-        if bin_dtype == "numerical":
-            col = Column(c, "int", fr.n_rows, dev=data, dev_valid=v, anv_dtype=_lib.ANV_I32,
-                         null_count=src.null_count)
-        else:
-            col = Column(c, "string", fr.n_rows, dev=(data - 1).clamp_(min=0), dev_valid=v, anv_dtype=_lib.ANV_I32,
-                         null_count=src.null_count, dictionary=_labels(cuts[i], len(cuts[0])))
-        if output_mode == "replace":
-            new_cols[c] = col
-        else:
-            col.name = c + "_binned"
-            new_cols[c + "_binned"] = col
-    odf = ColumnFrame(new_cols, fr.n_rows)
+    if getattr(fr, "is_partitioned", False):
+        # lazy per-chunk transform with the (global) model: the binned frame is partitioned like its input
+        schema = _apply_binning(fr._schema, cols, cuts, lohi, bin_dtype, output_mode)
+        odf = fr.map_chunks(schema, lambda ch: _apply_binning(ch, cols, cuts, lohi, bin_dtype, output_mode))
+    else:
+        odf = _apply_binning(fr, cols, cuts, lohi, bin_dtype, output_mode)
     if print_impact:
         from ..data_analyzer.stats_generator import uniqueCount_computation
         out_cols = cols if output_mode == "replace" else [c + "_binned" for c in cols]

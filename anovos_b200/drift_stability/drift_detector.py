@@ -113,6 +113,11 @@ def statistics(spark, idf_target, idf_source, list_of_cols="all", drop_cols=None
     if other:
         raise TypeError("columns %s have a dtype the drift path does not handle" % other)
 
+    if use_sampling and (getattr(tgt, "is_partitioned", False) or getattr(src, "is_partitioned", False)):
+        if tgt.count() > sample_size or (src is not None and src.count() > sample_size):
+            raise NotImplementedError("use_sampling=True is not implemented for row-partitioned frames: pass "
+                                      "use_sampling=False (the whole frame is cheap to scan on the GPU)")
+        use_sampling = False
     if use_sampling:
         if sample_method != "random" and (tgt.count() > sample_size or (src is not None and src.count() > sample_size)):
             raise NotImplementedError("only sample_method='random' is implemented on the B200 path")

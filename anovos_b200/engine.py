@@ -85,6 +85,8 @@ def _to_dev(arr: np.ndarray):
 
 def moments(frame: ColumnFrame, names):
     """-> structured ndarray (one row per name) with MOMENT_FIELDS.  One fused pass."""
+    if getattr(frame, "is_partitioned", False):
+        return frame.moments(names)
     global launch_count
     torch = _lib.require_cuda()
     L = _lib.lib()
@@ -179,6 +181,8 @@ class BinModel:
 
 def histogram(frame: ColumnFrame, model: BinModel):
     """-> uint64 ndarray [n_cols, max_bins + 1]: slot 0 = nulls, slot b = rows in bin b."""
+    if getattr(frame, "is_partitioned", False):
+        return frame.histogram(model)
     global launch_count
     _lib.require_cuda()
     L = _lib.lib()
@@ -197,6 +201,8 @@ def histogram(frame: ColumnFrame, model: BinModel):
 
 def moments_histogram(frame: ColumnFrame, model: BinModel):
     """Moments AND histogram of `model.names` in ONE read of the frame."""
+    if getattr(frame, "is_partitioned", False):
+        return frame.moments_histogram(model)
     global launch_count
     _lib.require_cuda()
     L = _lib.lib()
@@ -219,6 +225,8 @@ def moments_histogram(frame: ColumnFrame, model: BinModel):
 
 def bin_assign(frame: ColumnFrame, model: BinModel):
     """-> int32 CUDA tensor [n_cols, stride] of bin ids (0 = null row); stride >= n_rows."""
+    if getattr(frame, "is_partitioned", False):
+        return frame.bin_assign(model)
     global launch_count
     torch = _lib.require_cuda()
     L = _lib.lib()
@@ -239,6 +247,8 @@ def code_counts(frame: ColumnFrame, names):
     """Dictionary-code histograms of string columns -> list of uint64 arrays [cardinality + 1]
     (slot 0 = nulls).  Columns are grouped by cardinality class so each launch sizes its
     shared-memory histogram for its own group."""
+    if getattr(frame, "is_partitioned", False):
+        return frame.code_counts(list(names))
     global launch_count
     _lib.require_cuda()
     L = _lib.lib()
@@ -310,6 +320,8 @@ def quantile_ranks(n_valid: int, probs):
 def select_ranks(frame: ColumnFrame, names, ranks):
     """ranks: int64 array [n_cols, n_ranks] of 1-based ranks among non-null values (0 = skip).
     -> float64 array [n_cols, n_ranks] of the exact order statistics (NaN where skipped)."""
+    if getattr(frame, "is_partitioned", False):
+        return frame.select_ranks(names, ranks)
     global launch_count
     _lib.require_cuda()
     L = _lib.lib()
@@ -349,6 +361,8 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
     ranks: optional int64 [n_cols, n_ranks] of 1-based ranks among the non-null values (0 = skip);
     then returns (list, float64 [n_cols, n_ranks]) with the exact order statistics read from the
     sorted keys."""
+    if getattr(frame, "is_partitioned", False):
+        return frame.sort_mode_distinct(names, ranks)
     global launch_count
     torch = _lib.require_cuda()
     L = _lib.lib()
@@ -419,6 +433,22 @@ def hll_estimate_from_registers(regs: np.ndarray, p: int):
     return int(math.floor(e + 0.5)), True
 
 
+def hll_registers(frame: ColumnFrame, names, p: int):
+    """-> uint32 [n_cols, 2**p] HLL++ registers of NUMERIC columns (max-mergeable across row partitions)."""
+    if getattr(frame, "is_partitioned", False):
+        return frame.hll_registers(list(names), p)
+    global launch_count
+    _lib.require_cuda()
+    L = _lib.lib()
+    names = list(names)
+    m = 1 << p
+    desc, keep = frame.descriptors(names)
+    regs = _dev_bytes(len(names) * m * 4)
+    _call(L.anv_hll_registers, "anv_hll_registers", desc.data_ptr(), len(names), frame.n_rows, p, regs.data_ptr(), _stream())
+    launch_count += 1
+    return _host(regs).view(np.uint32)[:len(names) * m].reshape(len(names), m).copy()
+
+
 def hll_estimates(frame: ColumnFrame, names, p: int):
     """-> list of (estimate, in_bias_band) matching Spark's approx_count_distinct."""
     global launch_count
@@ -430,11 +460,7 @@ def hll_estimates(frame: ColumnFrame, names, p: int):
     num = [n for n in names if frame.column(n).kind == "num"]
     cat = [n for n in names if frame.column(n).kind == "cat"]
     if num:
-        desc, keep = frame.descriptors(num)
-        regs = _dev_bytes(len(num) * m * 4)
-        _call(L.anv_hll_registers, "anv_hll_registers", desc.data_ptr(), len(num), frame.n_rows, p, regs.data_ptr(), _stream())
-        launch_count += 1
-        R = _host(regs).view(np.uint32).reshape(len(num), m)
+        R = hll_registers(frame, num, p)
         for i, n in enumerate(num):
             out[n] = hll_estimate_from_registers(R[i], p)
     if cat:

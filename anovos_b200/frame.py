@@ -230,6 +230,31 @@ class ColumnFrame:
                             dictionary=c.dictionary)
         return ColumnFrame(out, m)
 
+    def slice_rows(self, r0: int, r1: int) -> "ColumnFrame":
+        """Zero-copy view of rows [r0, r1): r0 must be a multiple of 32 so that the validity
+        bitmap (and the 16-byte alignment of the values) slices on a word boundary.  Host-resident
+        columns stay on the host (each slice uploads on first use): the row chunks of a
+        PartitionedFrame are made this way."""
+        r0, r1 = int(r0), min(int(r1), self.n_rows)
+        if r0 % 32 or r0 < 0 or r1 < r0:
+            raise ValueError("slice_rows: r0 must be a non-negative multiple of 32 and r1 >= r0")
+        m = r1 - r0
+        w0, w1 = r0 // 32, (r1 + 31) // 32
+        out = OrderedDict()
+        for n, c in self._cols.items():
+            if c.kind == "other":
+                out[n] = Column(n, c.sdtype, m)
+                continue
+            host = c._host[r0:r1] if c._host is not None else None
+            hv = c._host_valid[w0:w1] if c._host_valid is not None else None
+            dev = c._dev[r0:r1] if c._dev is not None else None
+            dv = c._dev_valid[w0:w1] if c._dev_valid is not None else None
+            if c._ready is not None and dev is not None:  # slice of an in-flight upload: wait for it first
+                c.device()
+            out[n] = Column(n, c.sdtype, m, host=host, host_valid=hv, dev=dev, dev_valid=dv, anv_dtype=c.anv_dtype,
+                            dictionary=c.dictionary)
+        return ColumnFrame(out, m)
+
     def __contains__(self, name):
         return name in self._cols
 
@@ -349,7 +374,7 @@ class ColumnFrame:
 
 
 def as_frame(idf) -> ColumnFrame:
-    if isinstance(idf, ColumnFrame):
+    if isinstance(idf, ColumnFrame) or getattr(idf, "is_partitioned", False):
         return idf
     mod = type(idf).__module__
     if mod.startswith("pyarrow"):

@@ -125,6 +125,8 @@ def prefetch(frame: ColumnFrame, names=None, want=("moments", "mode", "hll"), rs
     (moments -> sort-based mode/distinct/percentiles -> HLL++) while groups g+1.. are still in
     flight over PCIe.  The stats functions called afterwards hit the cache.  On a frame that is
     already on the device this is just the batched passes."""
+    if getattr(frame, "is_partitioned", False):
+        return frame  # chunks are uploaded (and freed) pass by pass
     torch = _lib.require_cuda()
     names = [n for n in (names or frame.columns) if frame.column(n).kind != "other"]
     copy = torch.cuda.Stream()

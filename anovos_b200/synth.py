@@ -51,9 +51,10 @@ def column_params(c: int, seed: int, shifted: bool = False):
 
 
 def device_frame(rows: int, cols: int, seed: int = 42, first_col: int = 0, shifted: bool = False, cat_every: int = 0,
-                 prefix: str = "c") -> ColumnFrame:
+                 prefix: str = "c", row0: int = 0) -> ColumnFrame:
     """`cols` columns starting at global column id `first_col`; every `cat_every`-th column
-    (0 = none) is a dictionary-coded string column (Zipf s=1.2)."""
+    (0 = none) is a dictionary-coded string column (Zipf s=1.2).  row0 (multiple of 32): generate
+    the row chunk [row0, row0 + rows) of a larger frame, bit-identical to those rows of it."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -67,15 +68,15 @@ def device_frame(rows: int, cols: int, seed: int = 42, first_col: int = 0, shift
             rate = NULL_RATES[c % 4]
             x = torch.empty(rows, dtype=torch.int32, device="cuda")
             v = torch.zeros(words, dtype=torch.int32, device="cuda") if rate > 0 else None
-            _lib.check(L.anv_synth_codes(x.data_ptr(), v.data_ptr() if v is not None else None, rows, seed, c, card,
-                                         1.2, rate, st), "anv_synth_codes")
+            _lib.check(L.anv_synth_codes_rows(x.data_ptr(), v.data_ptr() if v is not None else None, rows, row0, seed, c,
+                                              card, 1.2, rate, st), "anv_synth_codes_rows")
             data[name] = (x, v, ["cat_%05d" % k for k in range(card)])
             continue
         fam, a, b, rate = column_params(c, 42, shifted)
         x = torch.empty(rows, dtype=torch.float32, device="cuda")
         v = torch.zeros(words, dtype=torch.int32, device="cuda") if rate > 0 else None
-        _lib.check(L.anv_synth_f32(x.data_ptr(), v.data_ptr() if v is not None else None, rows, seed, c, fam, a, b, rate,
-                                   st), "anv_synth_f32")
+        _lib.check(L.anv_synth_f32_rows(x.data_ptr(), v.data_ptr() if v is not None else None, rows, row0, seed, c, fam,
+                                        a, b, rate, st), "anv_synth_f32_rows")
         data[name] = (x, v) if v is not None else x
     return ColumnFrame.from_tensors(data, n_rows=rows)
 

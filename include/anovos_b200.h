@@ -145,6 +145,23 @@ size_t anv_select_workspace_bytes(int n_cols, int n_ranks);
 int anv_select_ranks(const anv_column_t* cols, int n_cols, int64_t n_rows, const int64_t* ranks,
                      int n_ranks, int key_bits, double* out, void* workspace, size_t workspace_bytes,
                      void* stream);
+/* The same selection, one radix pass at a time, for frames whose ROWS are partitioned (row chunks
+ * streamed through one GPU, or row slabs on several GPUs - SURVEY.md 8(e) "row-sharded variant":
+ * "quantile select needs one all-reduce per refinement round"):
+ *   anv_select_begin                       zero the histograms in the workspace
+ *   for pass in 0 .. anv_select_passes(key_bits)-1:
+ *     anv_select_accumulate(partition)     once per row partition: adds its digit histogram
+ *     [all-reduce(sum) the uint64 region anv_select_hist_region reports, across ranks]
+ *     anv_select_advance                   locate every rank's digit; the last pass writes `out`
+ * anv_select_ranks is exactly this sequence on one partition. */
+int anv_select_passes(int key_bits);
+int anv_select_begin(int n_cols, int n_ranks, void* workspace, size_t workspace_bytes, void* stream);
+int anv_select_hist_region(int n_cols, int n_ranks, int pass, size_t* offset, size_t* bytes);
+int anv_select_accumulate(const anv_column_t* cols, int n_cols, int64_t n_rows, int n_ranks,
+                          int key_bits, int pass, void* workspace, size_t workspace_bytes, void* stream);
+int anv_select_advance(const anv_column_t* cols, int n_cols, const int64_t* ranks, int n_ranks,
+                       int key_bits, int pass, double* out, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* ---- K6: HyperLogLog++ registers of approx_count_distinct(col, rsd) (stats_generator.py:
  *      605-608): Spark's XXH64 (seed 42) per-type encoding - I32 hashInt, I64 hashLong,
@@ -178,6 +195,13 @@ int anv_synth_f32(float* data, uint32_t* validity, int64_t n_rows, uint64_t seed
                   int family, float a, float b, float null_rate, void* stream);
 int anv_synth_codes(int32_t* data, uint32_t* validity, int64_t n_rows, uint64_t seed, uint32_t column,
                     int cardinality, float zipf_s, float null_rate, void* stream);
+/* The same generators for the row chunk [row0, row0 + n_rows) of a larger frame (row0 % 32 == 0):
+ * the chunk is bit-identical to those rows of the whole frame, so streamed / row-sharded runs
+ * see the same data as a resident one. */
+int anv_synth_f32_rows(float* data, uint32_t* validity, int64_t n_rows, int64_t row0, uint64_t seed,
+                       uint32_t column, int family, float a, float b, float null_rate, void* stream);
+int anv_synth_codes_rows(int32_t* data, uint32_t* validity, int64_t n_rows, int64_t row0, uint64_t seed,
+                         uint32_t column, int cardinality, float zipf_s, float null_rate, void* stream);
 
 #ifdef __cplusplus
 }
