@@ -140,10 +140,11 @@ def measures_of_counts(spark, idf, list_of_cols="all", drop_cols=[], print_impac
     fr = as_frame(idf)
     cols = _discrete_cols(fr, list_of_cols, drop_cols)
     N = fr.count()
-    m = profile.moments(fr, cols)
+    m = profile.moments(fr, [c for c in cols if fr.column(c).kind == "num"])
+    nv = profile.n_valid(fr, cols)       # string columns: from the code histogram when a pass already left one
     rows = []
     for c in cols:
-        fill = int(m[c]["n_valid"])
+        fill = nv[c]
         fill_pct = _R(fill / N)
         row = [c, fill, fill_pct, N - fill, _R(1 - fill_pct)]
         if fr.column(c).kind == "num":

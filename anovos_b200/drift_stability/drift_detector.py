@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import math
 import os
+import re
 
 import numpy as np
 import pandas as pd
@@ -36,11 +37,14 @@ def _freq_dir(model_path, col):
     return os.path.join(model_path, "frequency_counts", col)
 
 
+_NEEDS_QUOTES = re.compile(r'[,"\n\r]')
+
+
 def _csv_field(v):
     if v is None:
         return ""
-    s = str(v)
-    if any(ch in s for ch in ',"\n\r'):
+    s = v if type(v) is str else str(v)
+    if _NEEDS_QUOTES.search(s):
         s = '"' + s.replace('"', '""') + '"'
     return s
 
@@ -52,9 +56,22 @@ def _save_frequency(model_path, col, keys, p):
     for f in os.listdir(d):
         if f.endswith(".csv"):
             os.remove(os.path.join(d, f))
+    ks = list(map(_csv_field, keys))
+    vs = list(map(repr, np.asarray(p, dtype=np.float64).tolist()))
     with open(os.path.join(d, "part-00000.csv"), "w", newline="") as fh:
         fh.write(_csv_field(col) + ",p\n")
-        fh.write("".join("%s,%s\n" % (_csv_field(k), repr(float(v))) for k, v in zip(keys, p)))
+        if ks:
+            fh.write("\n".join(map(",".join, zip(ks, vs))) + "\n")
+
+
+def _utf8_sorted(fr, col):
+    """Is the dictionary of string column `col` in UTF-8 byte order (Spark's orderBy on strings)?  True for
+    frames built from Arrow / pandas; a hand-made dictionary is checked once."""
+    key = ("dict_utf8_sorted", col)
+    if key not in fr._cache:
+        b = [s.encode("utf-8") for s in fr.column(col).dictionary]
+        fr._cache[key] = all(x < y for x, y in zip(b, b[1:]))
+    return fr._cache[key]
 
 
 def _load_frequency(model_path, col):
@@ -157,7 +174,10 @@ def statistics(spark, idf_target, idf_source, list_of_cols="all", drop_cols=None
     tgt_num_counts = {}
     if binned:
         tm = engine.BinModel(tgt, binned, cuts, None if lohi is None else lohi)
-        _, ht = engine.moments_histogram(tgt, tm)                  # ONE read of the target frame
+        mt, ht = engine.moments_histogram(tgt, tm)                 # ONE read of the target frame
+        tc = profile._cache(tgt, "moments")                        # ... whose moments the stats functions reuse
+        for i, c in enumerate(binned):
+            tc.setdefault(c, mt[i])
         for i, c in enumerate(binned):
             tgt_num_counts[c] = ht[i, :len(cuts[i]) + 2]
     unbinned = [c for c in num_cols if c not in binned]            # all-null source columns (SURVEY C#12)
@@ -214,6 +234,21 @@ def statistics(spark, idf_target, idf_source, list_of_cols="all", drop_cols=None
                 T.append(t)
             else:
                 sdic, sh = src.column(c).dictionary, src_cat[c]
+                if (sdic is tdic or sdic == tdic) and _utf8_sorted(src, c):
+                    # same (UTF-8 ordered) dictionary on both sides - the usual case: the key union is a mask
+                    keep = np.flatnonzero((sh[1:] > 0) | (th[1:] > 0))
+                    s = np.concatenate([sh[:1], sh[1:][keep]]).astype(np.uint64)
+                    t = np.concatenate([th[:1], th[1:][keep]]).astype(np.uint64)
+                    S.append(s)
+                    T.append(t)
+                    if source_save:
+                        nz = np.flatnonzero(s[1:] > 0)
+                        kk = ([None] if s[0] > 0 else []) + [sdic[i] for i in keep[nz].tolist()]
+                        pp = np.concatenate([np.zeros(1 if s[0] > 0 else 0), s[1:][nz].astype(np.float64) / count_source])
+                        _save_frequency(model_path, c, kk, pp)
+                    kinds.append(1)
+                    order.append(c)
+                    continue
                 keys = sorted({sdic[i] for i in np.flatnonzero(sh[1:])} | {tdic[i] for i in np.flatnonzero(th[1:])},
                               key=lambda s: s.encode("utf-8"))        # orderBy(i): UTF-8 byte order
                 spos, tpos = {k: i for i, k in enumerate(sdic)}, {k: i for i, k in enumerate(tdic)}

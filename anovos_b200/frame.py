@@ -97,10 +97,10 @@ def _arrow_validity_words(arr):
 
 class Column:
     __slots__ = ("name", "sdtype", "kind", "anv_dtype", "n_rows", "null_count", "dictionary",
-                 "_host", "_host_valid", "_dev", "_dev_valid", "_ready")
+                 "_host", "_host_valid", "_dev", "_dev_valid", "_ready", "_loader")
 
     def __init__(self, name, sdtype, n_rows, host=None, host_valid=None, dev=None, dev_valid=None,
-                 anv_dtype=None, null_count=None, dictionary=None):
+                 anv_dtype=None, null_count=None, dictionary=None, loader=None):
         self.name, self.sdtype, self.kind = name, sdtype, kind_of(sdtype)
         self.n_rows = int(n_rows)
         self._host, self._host_valid, self._dev, self._dev_valid = host, host_valid, dev, dev_valid
@@ -108,6 +108,7 @@ class Column:
         self.null_count = null_count
         self.dictionary = dictionary
         self._ready = None  # CUDA event of an in-flight asynchronous upload
+        self._loader = loader  # () -> (device data, device validity | None): materialised on first use (lazy chunks)
 
     def upload_async(self, stream):
         """Enqueue the H2D copy of this column on `stream` (pinned host memory makes it truly
@@ -140,6 +141,8 @@ class Column:
 
     @property
     def has_validity(self):
+        if self._loader is not None and self._dev is None:
+            return self.null_count is None or self.null_count > 0
         return self._host_valid is not None or self._dev_valid is not None
 
     def device(self):
@@ -150,6 +153,8 @@ class Column:
         if self._ready is not None:  # asynchronous upload in flight: order the current stream after it
             torch.cuda.current_stream().wait_event(self._ready)
             self._ready = None
+        if self._dev is None and self._loader is not None:
+            self._dev, self._dev_valid = self._loader()
         if self._dev is None:
             global h2d_bytes
             h = self._host if self._host.flags.writeable else self._host.copy()
@@ -164,7 +169,7 @@ class Column:
         return self._dev, self._dev_valid
 
     def drop_device(self):
-        if self._host is not None:
+        if self._host is not None or self._loader is not None:
             self._dev = self._dev_valid = None
 
 
@@ -245,6 +250,8 @@ class ColumnFrame:
             if c.kind == "other":
                 out[n] = Column(n, c.sdtype, m)
                 continue
+            if c._dev is None and c._host is None and c._loader is not None:
+                c.device()   # a lazy column has to exist before it can be sliced
             host = c._host[r0:r1] if c._host is not None else None
             hv = c._host_valid[w0:w1] if c._host_valid is not None else None
             dev = c._dev[r0:r1] if c._dev is not None else None

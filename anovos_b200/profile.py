@@ -32,8 +32,10 @@ def moments(frame: ColumnFrame, names):
 def n_valid(frame: ColumnFrame, names):
     """Non-null counts of numeric AND categorical columns (dictionary codes are I32 columns,
     so the same fused pass counts them)."""
-    m = moments(frame, names)
-    return {n: int(m[n]["n_valid"]) for n in names}
+    cc = frame._cache.get("codes", {})
+    have = {n: frame.n_rows - int(cc[n][0]) for n in names if n in cc and n not in frame._cache.get("moments", {})}
+    m = moments(frame, [n for n in names if n not in have])
+    return {n: have[n] if n in have else int(m[n]["n_valid"]) for n in names}
 
 
 def quantiles(frame: ColumnFrame, names, probs):

@@ -30,6 +30,13 @@ WORKLOADS = {
     "c2": dict(rows=10_000_000, cols=50, desc="synthetic 10M rows x 50 float32 cols: full stats_generator"),
     "c3": dict(rows=100_000_000, cols=200, desc="synthetic 100M rows x 200 float32 cols: full stats_generator"),
     "tiny": dict(rows=200_000, cols=8, desc="smoke-size synthetic frame"),
+    # streamed workloads (BASELINE.json configs[3], [4]): the frames do not fit HBM, row chunks are (re)generated on the
+    # device pass by pass; step = drift statistics(all methods) + counts/shape of both frames from the same passes
+    "c4": dict(rows=100_000_000, cols=200, chunk=12_500_000, cat_every=4, stream=True,
+               desc="synthetic source 100M + target 100M rows x 200 mixed num/cat cols: drift_statistics PSI/HD/JSD/KS, streamed"),
+    "c5": dict(rows=1_000_000_000, cols=63, chunk=16_777_216, cat_every=0, stream=True,
+               desc="synthetic source 1B + target 1B rows x 63 float32 cols per GPU (504 on 8): fused stats + drift, streamed"),
+    "tiny_stream": dict(rows=300_000, cols=8, chunk=65_536, cat_every=4, stream=True, desc="smoke-size streamed drift"),
 }
 METRIC = "rows x cols / s, full stats_generator (+ HBM GB/s of the fused scan kernel)"
 CPU_SAMPLE_ROWS = 1_000_000
@@ -149,6 +156,8 @@ def _run_ours(args, out):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
     rows, cols = args.rows or wl["rows"], args.cols or wl["cols"]
+    if wl.get("stream"):
+        return _run_stream(args, out, wl, rows, cols, world, rank, local)
 
     def barrier():
         torch.cuda.synchronize()
@@ -262,6 +271,181 @@ def _run_ours(args, out):
         dist.destroy_process_group()
     if line is not None:
         out.emit(json.dumps(line))
+
+
+STREAM_METRIC = "rows x cols / s, streamed fused stats + drift_statistics (source + target, + HBM GB/s of the fused pass)"
+
+
+def _run_stream(args, out, wl, rows, cols, world, rank, local):
+    """BASELINE.json configs[3]/[4]: source and target frames larger than HBM, streamed in row chunks.
+    Step = drift_detector.statistics(method_type="all", use_sampling=False) on two PartitionedFrames
+    + measures_of_counts / measures_of_shape of both (served by the moments the drift passes leave
+    behind): source numeric columns are read twice (K1 min/max -> cutoffs on the host -> K2), the
+    target once (fused K1+K2), string columns once per frame.  rows*cols counts ONE frame, like the
+    resident drift extra.  The chunks are generated on the device inside the timed region (there
+    is nowhere to keep them): generation time is measured separately and reported."""
+    import tempfile
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import anovos.data_analyzer.stats_generator as sg
+    import anovos.drift_stability.drift_detector as dd
+    from anovos_b200 import engine, parallel, synth
+    chunk, cat_every = args.chunk or wl["chunk"], wl["cat_every"]
+    tmp = tempfile.mkdtemp()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def frames():
+        kw = dict(first_col=rank * cols, cat_every=cat_every)
+        return (synth.partitioned_frame(rows, cols, chunk, seed=42, **kw),
+                synth.partitioned_frame(rows, cols, chunk, seed=43, shifted=True, **kw))
+
+    def step():
+        src, tgt = frames()
+        r = [dd.statistics(None, tgt, src, method_type="all", use_sampling=False, source_path=tmp).toPandas()]
+        for f in (src, tgt):
+            r += [sg.measures_of_counts(None, f).toPandas(), sg.measures_of_shape(None, f).toPandas()]
+        if world > 1:
+            mat, _ = parallel.frames_to_matrix(r[:1])
+            parallel.gather_summaries(mat, device="cuda")
+        return r, src.passes + tgt.passes
+
+    def generation_only():
+        """The same chunk generation the step performs (every column of every pass), without kernels."""
+        src, tgt = frames()
+        num = [n for n in src.columns if src.column(n).kind == "num"]
+        cat = [n for n in src.columns if src.column(n).kind == "cat"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for f, plan in ((src, [num, num, cat]), (tgt, [num, cat])):
+            for names in plan:
+                if not names:
+                    continue
+                for ch in f.chunks(names):
+                    for n in names:
+                        ch.column(n).device()
+                    torch.cuda.current_stream().synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(max(args.warmup, 1) if rows > 50_000_000 else max(args.warmup, 3)):
+        step()
+    barrier()
+    engine.timer = engine.KernelTimer()
+    l0 = engine.launch_count
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res, passes = step()
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = engine.launch_count - l0
+    kt = engine.timer.totals()
+    engine.timer = None
+    gen_ms = generation_only()
+    t = torch.tensor([ms, gen_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step, gen_ms = float(t[0].item()) / args.steps, float(t[1].item())
+    value = rows * cols * world / (ms_per_step / 1e3)
+    src, _ = frames()
+    n_num = sum(1 for c in src.columns if src.column(c).kind == "num")
+    n_null = sum(1 for c in src.columns if src.column(c).kind == "num" and src.column(c).has_validity)
+    alg_bytes = rows * n_num * 4 + n_null * ((rows + 7) // 8)      # one read of the numeric columns of ONE frame
+    peak, peak_src = peaks()
+    kf = kt.get("anv_moments_hist", {"ms": 0.0, "calls": 0})
+    fused_ms = kf["ms"] / args.steps                                  # all chunks of the target frame, per step
+    achieved = alg_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None
+    n_chunks = -(-rows // (chunk // 32 * 32))
+    roofline = {"kernel": "scan_kernel<MOM+HIST> (anv_moments_hist: target pass, moments + 10-bin histogram in one read)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes // n_chunks, "ms_per_launch": fused_ms / n_chunks,
+                "launches_per_step": n_chunks, "share_of_step": kf["ms"] / ms if ms > 0 else None}
+    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
+                   "share_of_step": v["ms"] / ms} for k, v in sorted(kt.items())}
+    kernel_ms = sum(v["ms"] for v in kt.values()) / args.steps
+    line = None
+    if rank == 0:
+        e2e = cpu = None
+        if not args.no_extras:
+            e2e = stream_e2e(args, wl, min(rows, 20_000_000), cols, chunk, torch, tmp)
+            cpu = cpu_stream_baseline(min(cols, 50))
+        line = {"metric": STREAM_METRIC, "value": value, "unit": "rows*cols/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (on-device Philox, regenerated chunk by chunk INSIDE the timed region: the frames exceed HBM)",
+                "config": {"workload": args.workload + ": " + wl["desc"], "rows": rows, "cols_per_gpu": cols,
+                           "chunk_rows": chunk, "chunks_per_frame": n_chunks, "frame_passes_per_step": passes,
+                           "l2": "every chunk (%.1f GB) is larger than L2" % (chunk * cols * 4 / 1e9),
+                           "generation_ms_per_step": gen_ms, "kernel_ms_per_step": kernel_ms,
+                           "value_excluding_generation": rows * cols * world / (max(ms_per_step - gen_ms, 1e-9) / 1e3),
+                           "flagged_columns": int(res[0]["flagged"].sum()),
+                           "sharding": "columns per rank; rows streamed per rank; one all_gather of the drift table per step"},
+                "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                "kernels": kernels}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        out.emit(json.dumps(line))
+
+
+def stream_e2e(args, wl, rows, cols, chunk, torch, tmp):
+    """The streamed step from pinned HOST frames (bounded row sample): every pass uploads its chunks,
+    chunk i+1 in flight on the copy stream while chunk i is scanned."""
+    import anovos.data_analyzer.stats_generator as sg
+    import anovos.drift_stability.drift_detector as dd
+    from anovos_b200 import engine, frame as framemod, synth
+    from anovos_b200.partitioned import PartitionedFrame
+    chunk = min(chunk, max(32, rows // 4 // 32 * 32))
+    hosts = []
+    for seed, shifted in ((42, False), (43, True)):
+        fr = synth.device_frame(rows, cols, seed=seed, shifted=shifted, cat_every=wl["cat_every"])
+        hh = {}
+        for n, v in host_copy(fr, torch).items():
+            dic = fr.column(n).dictionary
+            if dic is None:
+                hh[n] = v
+            else:
+                hh[n] = (v[0], v[1], dic) if isinstance(v, tuple) else (v, None, dic)
+        hosts.append(hh)
+        del fr
+    torch.cuda.empty_cache()
+
+    def one():
+        src = PartitionedFrame.from_frame(framemod.ColumnFrame.from_tensors(hosts[0], n_rows=rows), chunk)
+        tgt = PartitionedFrame.from_frame(framemod.ColumnFrame.from_tensors(hosts[1], n_rows=rows), chunk)
+        r = [dd.statistics(None, tgt, src, method_type="all", use_sampling=False, source_path=tmp).toPandas()]
+        for f in (src, tgt):
+            r += [sg.measures_of_counts(None, f).toPandas(), sg.measures_of_shape(None, f).toPandas()]
+        return r
+
+    one()
+    torch.cuda.synchronize()
+    steps = 2
+    h0, d0 = framemod.h2d_bytes, engine.d2h_bytes
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": rows * cols / dt, "unit": "rows*cols/s", "ms_per_step": dt * 1e3, "rows": rows,
+            "h2d_bytes_per_step": (framemod.h2d_bytes - h0) // steps, "d2h_bytes_per_step": (engine.d2h_bytes - d0) // steps,
+            "steps": steps, "note": "bounded sample (%d rows per frame) of the streamed step from pinned host columns: "
+                                    "every pass re-uploads its chunks (source numeric columns twice), wall clock" % rows}
 
 
 def fused_pass_numbers(src, rows, cols, alg_bytes, peak, torch, engine):
@@ -393,6 +577,17 @@ def cpu_baseline(cols, with_drift=False, rows=CPU_SAMPLE_ROWS, workers=None):
     return out
 
 
+def cpu_stream_baseline(cols, rows=CPU_SAMPLE_ROWS):
+    from anovos_b200 import synth
+    from oracle import cpu_bench
+    workers = min(cols, os.cpu_count() or 1)
+    t, used = cpu_bench.time_stream_step(synth.host_table(rows, cols), synth.host_table(rows, cols, seed=43, shifted=True), workers)
+    return {"value": rows * cols / t, "unit": "rows*cols/s", "cores": used, "kind": "port", "host_cores": os.cpu_count(),
+            "sample": "source + target of %d rows x %d float32 cols, oracle drift statistics(all) + counts + shape of both "
+                      "frames (NumPy restatement of the Spark semantics, not Spark), one process per column, %.2f s"
+                      % (rows, cols, t)}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU path.  Spark/JVM are not installed on the box, so
     this is the oracle port on all host cores, on bounded samples of the same workload."""
@@ -406,16 +601,21 @@ def run_reference(args):
     from oracle import cpu_bench
     workers = min(cols, os.cpu_count() or 1)
     table = synth.host_table(rows, cols)
+    stream = bool(wl.get("stream"))
+    target = synth.host_table(rows, cols, seed=43, shifted=True) if stream else None
     times = []
     for i in range(max(args.warmup, 1) + args.steps):
-        t, _, used = cpu_bench.time_stats_generator(table, workers)
+        if stream:
+            t, used = cpu_bench.time_stream_step(table, target, workers)
+        else:
+            t, _, used = cpu_bench.time_stats_generator(table, workers)
         if i >= max(args.warmup, 1):
             times.append(t)
     dt = sum(times) / len(times)
     v = rows * cols / dt
     cpu = {"value": v, "unit": "rows*cols/s", "cores": used, "kind": "port",
            "sample": "%d rows x %d cols per step (bounded sample of %s)" % (rows, cols, args.workload)}
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "rows*cols/s", "n_gpus": args.gpus,
+    print(json.dumps({"impl": "reference", "metric": STREAM_METRIC if stream else METRIC, "value": v, "unit": "rows*cols/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                       "data": "synthetic (NumPy twin of the device generator)",
@@ -434,6 +634,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--cols", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0, help="rows per chunk of the streamed workloads (c4, c5)")
     ap.add_argument("--no-extras", action="store_true", help="profiling runs: skip e2e / cpu_baseline / fused extras")
     args = ap.parse_args()
     if args.impl == "reference":

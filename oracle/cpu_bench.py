@@ -33,6 +33,29 @@ def _drift_group(names):
     return len(names)
 
 
+def _stream_group(names):
+    """The streamed bench step (bench.py c4/c5): drift statistics(all) + counts and shape of both frames."""
+    from . import api as O
+    _drift_group(names)
+    for t in (_TABLE.select(names), _TARGET.select(names)):
+        O.measures_of_counts(t)
+        O.measures_of_shape(t)
+    return len(names)
+
+
+def time_stream_step(table, target, workers=None):
+    """Wall seconds of the streamed step over (table, target), columns spread over `workers` processes."""
+    global _TABLE, _TARGET
+    _TABLE, _TARGET = table, target
+    workers = workers or os.cpu_count() or 1
+    groups = _split(table.column_names, workers)
+    with mp.get_context("fork").Pool(len(groups)) as pool:
+        pool.map(_stats_group, [g[:1] for g in groups])  # warm the workers (imports), not timed
+        t0 = time.perf_counter()
+        pool.map(_stream_group, groups)
+        return time.perf_counter() - t0, len(groups)
+
+
 def _split(names, k):
     k = max(1, min(k, len(names)))
     return [names[i::k] for i in range(k)]

@@ -130,9 +130,18 @@ def test_code_counts_and_drift_reduce():
     src = [np.array([5, 0, 10, 20, 0, 7], np.uint64), np.array([0, 3, 3, 0], np.uint64), np.array([2, 0, 9], np.uint64)]
     tgt = [np.array([0, 4, 0, 25, 0, 9], np.uint64), np.array([0, 3, 3, 0], np.uint64), np.array([1, 4, 9], np.uint64)]
     kinds = [0, 0, 1]
-    ns, nt = 42, 38
+    # wide tables (string columns with many keys) take the CTA-per-column path: keys missing on either side,
+    # null groups on none / one / both sides, a table exactly one key past the narrow limit
+    for width, nulls_s, nulls_t, kind in ((97, 0, 0, 1), (5000, 3, 0, 1), (12001, 4, 9, 1), (300, 1, 1, 0)):
+        a = rng.integers(0, 50, width + 1).astype(np.uint64) * (rng.random(width + 1) < 0.8)
+        b = rng.integers(0, 50, width + 1).astype(np.uint64) * (rng.random(width + 1) < 0.8)
+        a[0], b[0] = nulls_s, nulls_t
+        src.append(a.astype(np.uint64))
+        tgt.append(b.astype(np.uint64))
+        kinds.append(kind)
+    ns, nt = 4200000, 3800000
     d = engine.drift_reduce(src, tgt, kinds, ns, nt)
-    for i in range(3):
+    for i in range(len(src)):
         sg = {k: int(v) for k, v in enumerate(src[i]) if k and v}
         tg = {k: int(v) for k, v in enumerate(tgt[i]) if k and v}
         nulls = 0
