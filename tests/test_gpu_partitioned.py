@@ -238,3 +238,18 @@ def test_two_ranks_row_slabs_match_single_frame(tmp_path):
     uw = sg.uniqueCount_computation(None, whole).toPandas()
     up = pd.concat([pd.DataFrame(a["exact_unique"]), pd.DataFrame(b["exact_unique"])], ignore_index=True)
     _same_table(uw, up)
+
+
+def test_nccl_row_slabs_on_two_gpus():
+    """The same checks over NCCL (device-side all_reduce of the select histograms, grouped P2P exchange);
+    needs two GPUs - skipped on a single-GPU box, where the gloo test above covers the logic."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+                        os.path.join(root, "scripts", "nccl_rowslab_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ROWSLAB-OK 2" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
