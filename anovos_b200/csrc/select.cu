@@ -10,8 +10,8 @@
 // memory); a tiny scan kernel locates, for each requested rank, the bin it falls in and
 // the residual rank inside it; passes 1.. refine 10 more bits, touching shared memory
 // only for values whose prefix matches one of the <= 16 (deduplicated) target prefixes,
-// filtered by a 4096-bit bitmap of the targets' top-12-bit buckets.  3 passes for 32-bit
-// keys, 7 for 64-bit keys; all counting is integer => deterministic.
+// found through a 4096-cell hash table of the target prefixes (one byte load + one compare).
+// 3 passes for 32-bit keys, 7 for 64-bit keys; all counting is integer => deterministic.
 #include "common.cuh"
 
 namespace anv {
@@ -76,9 +76,16 @@ struct SelParams {
 
 struct SelShared {  // declared ONCE in the kernel (statics inside the templated tile body would be replicated per instantiation)
   uint64_t prefix[SEL_MAX_RANKS];
-  uint32_t filter[(1 << SEL_BITS0) / 32];
+  uint32_t tbl[(1 << SEL_BITS0) / 4];  // byte table: hash(prefix) -> slot (0xFF = no target prefix hashes here)
   int nslots;
 };
+
+// 12-bit multiplicative hash of a decided-bits prefix (the top-12-bit bucket alone is a poor filter for
+// floats: it holds sign + exponent + 3 mantissa bits, so a handful of buckets cover most of a column)
+__device__ __forceinline__ uint32_t prefix_hash(uint64_t pf) {
+  const uint32_t x = (uint32_t)pf * 0x9E3779B1u + (uint32_t)(pf >> 32) * 0x85EBCA77u;
+  return x >> (32 - SEL_BITS0);
+}
 
 template <typename T, bool NULLS, bool FIRST>
 __device__ __forceinline__ void select_tile(const SelParams& P, const anv_column_t& col, int c, uint32_t* sh, SelShared& SS) {
@@ -93,39 +100,53 @@ __device__ __forceinline__ void select_tile(const SelParams& P, const anv_column
   const uint32_t dmask = (uint32_t)nbins - 1u;
 
   uint64_t* s_prefix = SS.prefix;
-  uint32_t* s_filter = SS.filter;
+  uint8_t* s_tbl = reinterpret_cast<uint8_t*>(SS.tbl);
   int& s_nslots = SS.nslots;
   int n_slots = 1;
   if (!FIRST) {
     const SelState& S = P.state[c];
     if (tid == 0) s_nslots = S.n_slots;
-    for (int i = tid; i < (1 << SEL_BITS0) / 32; i += ANV_BLOCK) s_filter[i] = 0;
+    for (int i = tid; i < (1 << SEL_BITS0) / 4; i += ANV_BLOCK) SS.tbl[i] = 0xFFFFFFFFu;
     __syncthreads();
     n_slots = s_nslots;
     if (n_slots == 0) return;  // nothing requested for this column (uniform per CTA)
-    if (tid < n_slots) {
-      const uint64_t pf = S.slot_prefix[tid];
-      s_prefix[tid] = pf;
-      const int decided = 64 - (P.shift + P.bits);  // number of prefix bits
-      const uint32_t top = (uint32_t)(pf >> (decided - SEL_BITS0));
-      atomicOr(&s_filter[top >> 5], 1u << (top & 31));
+    if (tid < n_slots) s_prefix[tid] = S.slot_prefix[tid];
+    __syncthreads();
+    if (tid == 0) {  // first slot wins a hash cell (deterministic); colliding prefixes fall back to the linear search
+      for (int q = 0; q < n_slots; ++q) {
+        const uint32_t h = prefix_hash(s_prefix[q]);
+        if (s_tbl[h] == 0xFFu) s_tbl[h] = (uint8_t)q;
+      }
     }
   }
   for (int i = tid; i < n_slots * nbins; i += ANV_BLOCK) sh[i] = 0;
   __syncthreads();
 
+  // Per-thread run aggregation: a heavy value (e.g. the 70% exact zeros of a zero-inflated column) lands
+  // in ONE counter; consecutive hits of the same counter are added once instead of serialising the
+  // whole CTA on one shared-memory address.
+  uint32_t run_idx = 0xffffffffu, run_cnt = 0;
+  auto count = [&](uint32_t idx) {
+    if (idx == run_idx) { ++run_cnt; return; }
+    if (run_cnt) atomicAdd(&sh[run_idx], run_cnt);
+    run_idx = idx; run_cnt = 1;
+  };
   auto elem = [&](T x, bool valid) {
     if (NULLS && !valid) return;
     const uint64_t k = sort_key<T>(x);
     const uint32_t d = (uint32_t)(k >> P.shift) & dmask;
     if (FIRST) {
-      atomicAdd(&sh[d], 1u);
+      count(d);
     } else {
-      const uint32_t top = (uint32_t)(k >> (64 - SEL_BITS0));
-      if ((s_filter[top >> 5] >> (top & 31)) & 1u) {
-        const uint64_t pf = k >> (P.shift + P.bits);
-        for (int s = 0; s < n_slots; ++s)
-          if (s_prefix[s] == pf) { atomicAdd(&sh[s * nbins + d], 1u); break; }
+      const uint64_t pf = k >> (P.shift + P.bits);
+      const uint32_t cand = s_tbl[prefix_hash(pf)];
+      if (cand != 0xFFu) {
+        if (s_prefix[cand] == pf) {
+          count(cand * (uint32_t)nbins + d);
+        } else {  // hash collision between two target prefixes, or a foreign prefix in a used cell: rare
+          for (int s = 0; s < n_slots; ++s)
+            if (s_prefix[s] == pf) { count((uint32_t)(s * nbins) + d); break; }
+        }
       }
     }
   };
@@ -171,6 +192,7 @@ __device__ __forceinline__ void select_tile(const SelParams& P, const anv_column
       elem(data[row], valid);
     }
   }
+  if (run_cnt) atomicAdd(&sh[run_idx], run_cnt);
   __syncthreads();
   unsigned long long* out = P.hist + (size_t)c * P.n_ranks * (1 << SEL_BITS);
   if (FIRST) out = P.hist + (size_t)c * (1 << SEL_BITS0);
