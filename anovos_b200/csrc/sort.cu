@@ -235,43 +235,63 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortParams<K> P) 
   const int c = blockIdx.x, tid = threadIdx.x;
   ColState& S = P.state[c];
   __shared__ int s_skip;
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t s_carry;
-  if (tid == 0) { s_skip = 0; s_carry = 0; }
+  __shared__ uint32_t wsum[2][33];   // double-buffered warp totals (+ chunk total): 2 barriers per chunk
+  if (tid == 0) s_skip = 0;
   __syncthreads();
   const unsigned long long n = S.n_valid;
   uint32_t* a = P.tile_hist + (size_t)c * 256 * P.n_tiles;
-  const int64_t total = (int64_t)256 * P.n_tiles;
+  const int64_t total = (int64_t)256 * P.n_tiles;   // a multiple of 256: every 16-entry group is whole
   if (n > 0) {
-    for (int64_t base = 0; base < total; base += 1024 * 4) {
-      uint32_t v[4], run = 0;
-      const int64_t i0 = base + (int64_t)tid * 4;
+    constexpr int PER = 16;                           // entries per thread per chunk (4 x 128-bit)
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t carry = 0;
+    int buf = 0;
+    for (int64_t base = 0; base < total; base += 1024 * PER, buf ^= 1) {
+      uint32_t v[PER], run = 0;
+      const int64_t i0 = base + (int64_t)tid * PER;
+      const bool in = i0 < total;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < total) ? a[i0 + k] : 0u; run += v[k]; }
+      for (int k = 0; k < PER / 4; ++k) {
+        const uint4 q = in ? *reinterpret_cast<const uint4*>(a + i0 + 4 * k) : make_uint4(0u, 0u, 0u, 0u);
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        run += q.x + q.y + q.z + q.w;
+      }
       uint32_t inc = run;
+#pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o);
-        if ((tid & 31) >= o) inc += t;
+        if (lane >= o) inc += t;
       }
-      if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+      if (lane == 31) wsum[buf][warp] = inc;
       __syncthreads();
       if (tid < 32) {
-        uint32_t w = wsum[tid], wi = w;
+        const uint32_t w = wsum[buf][tid];
+        uint32_t wi = w;
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const uint32_t t = __shfl_up_sync(ANV_FULL, wi, o);
           if (tid >= o) wi += t;
         }
-        wsum[tid] = wi - w;  // exclusive
+        wsum[buf][tid] = wi - w;  // exclusive
+        if (tid == 31) wsum[buf][32] = wi;
       }
       __syncthreads();
-      uint32_t ex = s_carry + wsum[tid >> 5] + inc - run;
+      uint32_t ex = carry + wsum[buf][warp] + inc - run;
+      if (in) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { if (i0 + k < total) a[i0 + k] = ex; ex += v[k]; }
-      __syncthreads();
-      if (tid == 1023) s_carry = ex;
-      __syncthreads();
+        for (int k = 0; k < PER / 4; ++k) {
+          uint4 q;
+          q.x = ex; ex += v[4 * k];
+          q.y = ex; ex += v[4 * k + 1];
+          q.z = ex; ex += v[4 * k + 2];
+          q.w = ex; ex += v[4 * k + 3];
+          *reinterpret_cast<uint4*>(a + i0 + 4 * k) = q;
+        }
+      }
+      carry += wsum[buf][32];
     }
   }
+  __syncthreads();
   // a digit whose total is n (its segment spans the whole prefix range) makes the pass a no-op: skip the scatter
   if (tid < 256 && n > 0) {
     const unsigned long long lo = a[(size_t)tid * P.n_tiles];
@@ -308,7 +328,6 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
   K* __restrict__ out = (src ? P.buf[0] : P.buf[1]) + (size_t)c * P.stride;
   __shared__ uint16_t wcnt[SCAT_WARPS][256];  // <= 4096 keys per tile: 16 bits are enough
   __shared__ uint32_t gbase[256];
-  __shared__ uint32_t dstart[256];
   __shared__ uint32_t wtot[8];
   __shared__ K sk[SORT_TILE];
   for (int i = tid; i < SCAT_WARPS * 256 / 2; i += SCAT_THREADS) reinterpret_cast<uint32_t*>(&wcnt[0][0])[i] = 0;
@@ -365,7 +384,12 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
       uint32_t woff = 0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) woff += (w < warp) ? wtot[w] : 0u;
-      dstart[tid] = woff + inc - total;
+      const uint32_t ds = woff + inc - total;
+      // fold the digit's start into the per-warp offsets (one lookup when placing) and keep a single
+      // "global base minus tile start" table for the copy-out (one lookup per key there as well)
+#pragma unroll
+      for (int w = 0; w < SCAT_WARPS; ++w) wcnt[w][tid] = (uint16_t)(wcnt[w][tid] + ds);
+      gbase[tid] -= ds;
     }
   }
   __syncthreads();
@@ -373,14 +397,13 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
   for (int r = 0; r < WR; ++r) {
     if (peers[r]) {
       const uint32_t d = digit_of(key[r], P.pass);
-      sk[dstart[d] + wcnt[warp][d] + pos[r]] = key[r];
+      sk[wcnt[warp][d] + pos[r]] = key[r];
     }
   }
   __syncthreads();
   for (int p = tid; p < nt; p += SCAT_THREADS) {
     const K k = sk[p];
-    const uint32_t d = digit_of(k, P.pass);
-    out[(size_t)gbase[d] + (p - dstart[d])] = k;
+    out[(size_t)(gbase[digit_of(k, P.pass)] + (uint32_t)p)] = k;
   }
 }
 

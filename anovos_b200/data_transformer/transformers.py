@@ -58,7 +58,7 @@ def compute_cutoffs(fr: ColumnFrame, cols, method_type, bin_size):
     if method_type == "equal_frequency":
         width = 1 / bin_size
         probs = [j * width for j in range(1, bin_size)]               # :211-214 (float artefacts kept)
-        q = profile.quantiles(fr, cols, probs)
+        q = profile.quantiles(fr, cols, probs, profile.APPROX_QUANTILE_EPS)   # approxQuantile(cols, probs, 0.01), :215
         cuts = [[float("nan") if v is None else float(v) for v in q[c]] for c in cols]
         return list(cols), cuts, [None] * len(cols)
     kept, cuts, lohi, dropped = [], [], [], []

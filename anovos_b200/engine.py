@@ -312,9 +312,13 @@ def drift_reduce(src_counts, tgt_counts, kinds, n_src, n_tgt, src_p=None):
 
 # ---- K4 ---------------------------------------------------------------------------------
 
-def quantile_ranks(n_valid: int, probs):
-    """Spark rank rule: 1-based rank max(1, ceil(p * n)) with p * n in float64."""
-    return [max(1, int(math.ceil(p * n_valid))) if n_valid > 0 else 0 for p in probs]
+def quantile_ranks(n_valid: int, probs, eps=None):
+    """1-based ranks of the order statistics Spark returns for `probs` over n_valid non-null values.
+    eps None: the exact rule max(1, ceil(p * n)) with p * n in float64.  eps = the relativeError of
+    the Spark call being replaced (1e-4 for summary(), 0.01 for approxQuantile): the Greenwald-Khanna sketch
+    position for one partition of < 50 000 values, the exact rule beyond (shared/gk.py)."""
+    from .shared import gk
+    return gk.spark_ranks(int(n_valid), probs, eps)
 
 
 def select_ranks(frame: ColumnFrame, names, ranks):

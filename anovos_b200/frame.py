@@ -77,6 +77,17 @@ def _pack_validity(valid_bool: np.ndarray) -> np.ndarray:
     return bits.view(np.int32)
 
 
+def pack_bits_device(bits):
+    """bool CUDA tensor [n] -> Arrow LSB-first validity bitmap as int32 words on the device."""
+    import torch
+    n = int(bits.numel())
+    words = (n + 31) // 32
+    padded = torch.zeros(words * 32, dtype=torch.int64, device=bits.device)
+    padded[:n] = bits.to(torch.int64)
+    w = (padded.view(words, 32) << torch.arange(32, device=bits.device, dtype=torch.int64)).sum(dim=1)
+    return (w & 0xFFFFFFFF).to(torch.int64).where(w < (1 << 31), w - (1 << 32)).to(torch.int32)
+
+
 def _arrow_validity_words(arr):
     """Arrow array -> int32 bitmap words (None when the array has no nulls)."""
     if arr.null_count == 0:
@@ -207,17 +218,19 @@ class ColumnFrame:
         names = set(names[0]) if len(names) == 1 and isinstance(names[0], (list, tuple, set)) else set(names)
         return ColumnFrame(OrderedDict((n, c) for n, c in self._cols.items() if n not in names), self.n_rows)
 
-    def dropna(self, subset=None) -> "ColumnFrame":
-        """`idf.dropna(subset=cols)`: keep the rows whose `subset` columns are all non-null (frame
-        transform on the device with torch indexing: plumbing, not a hot path)."""
+    def valid_mask(self, name):
+        """bool CUDA tensor [n_rows]: True where column `name` is non-null (frame transforms only)."""
         torch = _lib.require_cuda()
-        subset = list(subset) if subset is not None else self.columns
-        keep = torch.ones(self.n_rows, dtype=torch.bool, device="cuda")
+        d, v = self._cols[name].device()
+        if v is None:
+            return torch.ones(self.n_rows, dtype=torch.bool, device="cuda")
         rows = torch.arange(self.n_rows, device="cuda")
-        for n in subset:
-            d, v = self._cols[n].device()
-            if v is not None:
-                keep &= ((v[rows >> 5] >> (rows & 31).to(torch.int32)) & 1).bool()
+        return ((v[rows >> 5] >> (rows & 31).to(torch.int32)) & 1).bool()
+
+    def filter_rows(self, keep) -> "ColumnFrame":
+        """`idf.where(cond)`: keep the rows where the bool CUDA tensor `keep` is True (frame transform on the
+        device with torch indexing: plumbing, not a hot path)."""
+        torch = _lib.require_cuda()
         idx = torch.nonzero(keep).flatten()
         m = int(idx.numel())
         out = OrderedDict()
@@ -228,12 +241,22 @@ class ColumnFrame:
             d, v = c.device()
             nv = None
             if v is not None:
-                bits = ((v[idx >> 5] >> (idx & 31).to(torch.int32)) & 1).to(torch.uint8).cpu().numpy().astype(bool)
-                if not bits.all():
-                    nv = torch.from_numpy(_pack_validity(bits)).cuda()
+                bits = ((v[idx >> 5] >> (idx & 31).to(torch.int32)) & 1).bool()
+                if not bool(bits.all()):
+                    nv = pack_bits_device(bits)
             out[n] = Column(n, c.sdtype, m, dev=d.index_select(0, idx), dev_valid=nv, anv_dtype=c.anv_dtype,
                             dictionary=c.dictionary)
         return ColumnFrame(out, m)
+
+    def dropna(self, subset=None) -> "ColumnFrame":
+        """`idf.dropna(subset=cols)`: keep the rows whose `subset` columns are all non-null."""
+        torch = _lib.require_cuda()
+        subset = list(subset) if subset is not None else self.columns
+        keep = torch.ones(self.n_rows, dtype=torch.bool, device="cuda")
+        for n in subset:
+            if self._cols[n].kind != "other" and self._cols[n].device()[1] is not None:
+                keep &= self.valid_mask(n)
+        return self.filter_rows(keep)
 
     def slice_rows(self, r0: int, r1: int) -> "ColumnFrame":
         """Zero-copy view of rows [r0, r1): r0 must be a multiple of 32 so that the validity

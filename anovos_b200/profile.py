@@ -9,6 +9,7 @@ import numpy as np
 
 from . import _lib, engine
 from .frame import ColumnFrame
+from .shared.gk import APPROX_QUANTILE_EPS, SUMMARY_EPS
 
 
 SUMMARY_PROBS = [0.01, 0.05, 0.1, 0.25, 0.5, 0.75, 0.9, 0.95, 0.99]
@@ -38,17 +39,18 @@ def n_valid(frame: ColumnFrame, names):
     return {n: have[n] if n in have else int(m[n]["n_valid"]) for n in names}
 
 
-def quantiles(frame: ColumnFrame, names, probs):
-    """dict name -> list of exact order statistics at rank max(1, ceil(p*n)) (None if empty)."""
+def quantiles(frame: ColumnFrame, names, probs, eps=SUMMARY_EPS):
+    """dict name -> list of order statistics (None if empty) at the ranks Spark returns for `probs`: eps is the
+    relativeError of the replaced call (summary(): 1e-4, approxQuantile(..., 0.01): 0.01), see shared/gk.py."""
     c = _cache(frame, "quantiles")
     mom = moments(frame, names)
     want, extra = {}, {}
     for n in names:
         nv = int(mom[n]["n_valid"])
-        want[n] = engine.quantile_ranks(nv, probs)
+        want[n] = engine.quantile_ranks(nv, probs, eps)
         # a select pass costs the same for 1 or 16 ranks: always resolve the nine summary()
         # percentiles too, so median / IQR / percentiles share ONE radix select per column
-        extra[n] = engine.quantile_ranks(nv, SUMMARY_PROBS)
+        extra[n] = engine.quantile_ranks(nv, SUMMARY_PROBS, SUMMARY_EPS)
     todo = [n for n in names if any(r and (n, r) not in c for r in want[n])]
     if todo:
         sets = {n: sorted(set(r for r in want[n] + extra[n] if r and (n, r) not in c)) for n in todo}
@@ -99,7 +101,7 @@ def mode_distinct(frame: ColumnFrame, names):
         # well, so a full stats_generator run never needs a separate selection pass
         mom = moments(frame, num)
         qc = _cache(frame, "quantiles")
-        rk = np.array([engine.quantile_ranks(int(mom[n]["n_valid"]), SUMMARY_PROBS) for n in num], dtype=np.int64)
+        rk = np.array([engine.quantile_ranks(int(mom[n]["n_valid"]), SUMMARY_PROBS, SUMMARY_EPS) for n in num], dtype=np.int64)
         res, vals = engine.sort_mode_distinct(frame, num, rk)
         for i, n in enumerate(num):
             c[n] = res[i]

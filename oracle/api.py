@@ -69,6 +69,9 @@ def _resolve(table, list_of_cols, drop_cols, default, universe=None, allow_empty
     return cols
 
 
+_GK_CACHE = {}
+
+
 class ColumnProfile:
     """Everything the stats functions need from one column (float64 semantics)."""
 
@@ -114,10 +117,18 @@ class ColumnProfile:
             return (float(nn.min()) if nn.size else float("nan")), float("nan")
         return float(x.min()), float(x.max())
 
-    def quantile(self, p):
+    def quantile(self, p, eps=S.SUMMARY_EPS):
+        """summary() percentile (eps 1e-4) or approxQuantile(..., eps): Spark's sketch position for one partition
+        of < 50 000 values, the exact rank otherwise (S.approx_quantile_rank)."""
         if self.n == 0:
             return None
-        return float(S.quantile_sorted(self.sorted64, p))
+        key = (self.n, eps)
+        if key not in _GK_CACHE:
+            _GK_CACHE[key] = S.gk_single_batch_summary(self.n, eps) if (eps is not None and self.n < S.GK_HEAD_SIZE) else None
+        sm = _GK_CACHE[key]
+        if sm is None:
+            return float(S.quantile_sorted(self.sorted64, p))
+        return float(self.sorted64[S.gk_query_position(sm, self.n, eps, p)])
 
     def nonzero(self):
         if self.n == 0:
@@ -792,3 +803,116 @@ def IG_calculation(table, list_of_cols="all", drop_cols=[], label_col="label", e
                 s += -(tc / n) * (p * math.log2(p) + (1 - p) * math.log2(1 - p))
         rows.append([c, total_entropy - s])
     return pd.DataFrame(rows, columns=["attribute", "ig"])
+
+
+# ---------------------------------------------------------------------------
+# quality_checker.outlier_detection (data_analyzer/quality_checker.py:550-1045)
+# ---------------------------------------------------------------------------
+
+_DEFAULT_OUTLIER_CFG = {"pctile_lower": 0.05, "pctile_upper": 0.95, "stdev_lower": 3.0, "stdev_upper": 3.0,
+                        "IQR_lower": 1.5, "IQR_upper": 1.5, "min_validation": 2}
+
+
+def outlier_methodologies(detection_side, detection_configs):
+    """:788-830 -> (methodologies, min_validation); raises the reference's TypeErrors."""
+    sides = {"lower": ["lower"], "upper": ["upper"], "both": ["lower", "upper"]}[detection_side]
+    check = {m: {"lower": 0, "upper": 0} for m in ("pctile", "stdev", "IQR")}
+    for m in check:
+        for s in sides:
+            if m + "_" + s in detection_configs:
+                check[m][s] = 1
+    methods = []
+    for m, val in check.items():
+        vals = list(val.values())
+        if detection_side == "both":
+            if vals in ([1, 0], [0, 1]):
+                raise TypeError("Invalid input for detection_configs. If detection_side is 'both', the methodologies "
+                                "used on both sides should be the same")
+            if vals[0]:
+                methods.append(m)
+        elif val[detection_side]:
+            methods.append(m)
+    if "min_validation" in detection_configs:
+        if detection_configs["min_validation"] > len(methods):
+            raise TypeError("Invalid input for min_validation of detection_configs. It cannot be larger than the total "
+                            "number of methodologies on any side that detection will be applied over.")
+        n = detection_configs["min_validation"]
+    else:
+        n = len(methods)
+    return methods, n
+
+
+def outlier_bounds(table, cols, detection_side="upper", detection_configs=_DEFAULT_OUTLIER_CFG):
+    """-> (kept cols, [[lower|None, upper|None]], skewed cols).  Percentiles follow approxQuantile(cols, p, 0.01)
+    (:845,883) through S.approx_quantile_rank: the GK sketch position for one partition of < 50 000 values (this
+    reproduces all 13 pinned counts / clamp values of test_quality_checker.py:526-637), the exact rank beyond."""
+    methods, n = outlier_methodologies(detection_side, detection_configs)
+    prof = _profiles(table, cols)
+    pl, pu = detection_configs.get("pctile_lower", 0.05), detection_configs.get("pctile_upper", 0.95)
+    E = S.APPROX_QUANTILE_EPS
+    pct = {c: [prof[c].quantile(pl, E), prof[c].quantile(pu, E)] for c in cols}
+    skewed = [c for c in cols if pct[c][0] == pct[c][1]]
+    kept = [c for c in cols if c not in skewed]
+    params = []
+    for c in kept:
+        p = prof[c]
+        x = pct[c] if "pctile" in methods else [None, None]
+        y = [None, None]
+        if "stdev" in methods:
+            cnt, mean, m2, _, _ = S.central_moments(p.x64)
+            sd = S.stddev_samp(cnt, m2)
+            sd = float("nan") if sd is None else sd
+            y = [mean - detection_configs.get("stdev_lower", 0.0) * sd, mean + detection_configs.get("stdev_upper", 0.0) * sd]
+        z = [None, None]
+        if "IQR" in methods:
+            q1, q3 = p.quantile(0.25, E), p.quantile(0.75, E)
+            z = [q1 - detection_configs.get("IQR_lower", 0.0) * (q3 - q1), q3 + detection_configs.get("IQR_upper", 0.0) * (q3 - q1)]
+        lower = sorted([i for i in (x[0], y[0], z[0]) if i is not None], reverse=True)[n - 1]
+        upper = sorted([i for i in (x[1], y[1], z[1]) if i is not None])[n - 1]
+        params.append([lower, None] if detection_side == "lower" else ([None, upper] if detection_side == "upper" else [lower, upper]))
+    return kept, params, skewed
+
+
+def outlier_detection(table, list_of_cols="all", drop_cols=[], detection_side="upper", detection_configs=None,
+                      treatment=True, treatment_method="value_replacement", output_mode="replace", params=None):
+    """-> (treated pyarrow table, odf_print pandas [attribute, lower_outliers, upper_outliers,
+    excluded_due_to_skewness]).  `params` = (cols, bounds, skewed) of a saved model instead of computing them."""
+    cfg = dict(_DEFAULT_OUTLIER_CFG if detection_configs is None else detection_configs)
+    num = [f.name for f in table.schema if ColumnProfile(table.slice(0, 0), f.name).is_num]
+    cols = _dedupe(num if (isinstance(list_of_cols, str) and list_of_cols == "all") else _split(list_of_cols), _split(drop_cols))
+    if any(c not in num for c in cols):
+        raise TypeError("Invalid input for Column(s)")
+    if detection_side not in ("upper", "lower", "both"):
+        raise TypeError("Invalid input for detection_side")
+    if treatment_method not in ("null_replacement", "row_removal", "value_replacement"):
+        raise TypeError("Invalid input for treatment_method")
+    kept, bounds, skewed = params if params is not None else outlier_bounds(table, cols, detection_side, cfg)
+    rows, flags, new_cols = [], {}, {}
+    for c, (lo, hi) in zip(kept, bounds):
+        vals, valid = S.column_values(table, c)
+        v = vals.astype(np.float64)
+        with np.errstate(invalid="ignore"):
+            low = valid & ((v - lo) < 0) if lo is not None and detection_side in ("lower", "both") else np.zeros(len(v), bool)
+            up = valid & ((v - hi) > 0) if hi is not None and detection_side in ("upper", "both") else np.zeros(len(v), bool)
+        flags[c] = low | up
+        rows.append((c, int(low.sum()), int(up.sum()), 0))
+        if treatment and treatment_method == "value_replacement":
+            out = v.copy()
+            out[low], out[up] = (lo if lo is not None else 0.0), (hi if hi is not None else 0.0)
+            new_cols[c] = pa.array(out, mask=~valid)
+        elif treatment and treatment_method == "null_replacement":
+            new_cols[c] = pa.array(vals, mask=~valid | low | up)
+    rows += [(c, 0, 0, 1) for c in skewed]
+    odf = table
+    if treatment and treatment_method == "row_removal":
+        keep = np.ones(table.num_rows, bool)
+        for c in kept:
+            keep &= ~flags[c]
+        odf = table.filter(pa.array(keep))
+    elif treatment:
+        for c, arr in new_cols.items():
+            if output_mode == "replace":
+                odf = odf.set_column(odf.schema.get_field_index(c), c, arr)
+            else:
+                odf = odf.append_column(c + "_outliered", arr)
+    return odf, pd.DataFrame(rows, columns=["attribute", "lower_outliers", "upper_outliers", "excluded_due_to_skewness"])

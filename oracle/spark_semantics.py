@@ -236,6 +236,84 @@ def quantile_sorted(sorted_vals: np.ndarray, p: float):
     return sorted_vals[quantile_rank(p, n) - 1]
 
 
+# ---------------------------------------------------------------------------
+# Spark's Greenwald-Khanna sketch (org.apache.spark.sql.catalyst.util.QuantileSummaries, Spark >= 3.1;
+# un-vendored third-party code: restated from its published algorithm) as it behaves for ONE partition of
+# fewer than 50 000 non-null values - the situation of every unit test of the reference.  All values then sit
+# in the head buffer (defaultHeadSize = 50 000) until the final compress(): they are sorted and inserted in one
+# batch with g = 1 and delta_k = floor(2*eps*k) (0 for the first and the last), compressed once from the tail with
+# mergeThreshold = 2*eps*n, and queried with targetError = max(g + delta) / 2.  The surviving sample POSITIONS
+# and the queried position depend on (n, eps, p) only - never on the values - so approxQuantile / summary()
+# percentiles reduce to "the order statistic at a shifted rank".  Pinned by the 13 outlier counts / clamp values
+# of test_quality_checker.py:526-637 (eps = 0.01), which the exact rank ceil(p*n) does NOT reproduce.
+# Larger or multi-partition inputs make Spark's answer depend on arrival order and partitioning (any element
+# within eps*n ranks): there the exact rank is used.
+# ---------------------------------------------------------------------------
+
+GK_HEAD_SIZE = 50000
+
+
+def gk_single_batch_summary(n: int, eps: float):
+    """-> list of (position in the sorted values [0-based], g, delta) after withHeadBufferInserted + compress."""
+    if n <= 0:
+        return []
+    delta = [0] * n
+    for k in range(1, n - 1):                    # currentCount after the increment = k + 1
+        delta[k] = int(math.floor(2 * eps * (k + 1)))
+    thr = 2 * eps * n                            # mergeThreshold of compressImmut
+    res = []
+    head = [n - 1, 1, delta[n - 1]]              # the last element is always kept
+    for i in range(n - 2, 0, -1):                # the first element is never compressed
+        if 1 + head[1] + head[2] < thr:          # sample1.g + head.g + head.delta < mergeThreshold
+            head[1] += 1
+        else:
+            res.append(tuple(head))
+            head = [i, 1, delta[i]]
+    res.append(tuple(head))
+    if n > 1:
+        res.append((0, 1, 0))                    # "if necessary, add the minimum element"
+    res.reverse()
+    return res
+
+
+def gk_query_position(summary, n: int, eps: float, p: float) -> int:
+    """QuantileSummaries.query -> 0-based position in the sorted values."""
+    if p <= eps:
+        return summary[0][0]
+    if p >= 1 - eps:
+        return summary[-1][0]
+    target_error = max(g + d for _, g, d in summary) / 2.0
+    rank = int(math.ceil(p * n))
+    min_rank = summary[0][1]
+    i = 0
+    while i < len(summary) - 1:
+        pos, g, d = summary[i]
+        max_rank = min_rank + d
+        if max_rank - target_error <= rank <= min_rank + target_error:
+            return pos
+        i += 1
+        min_rank += summary[i][1]
+    return summary[-1][0]
+
+
+def approx_quantile_rank(p: float, n: int, eps) -> int:
+    """1-based rank Spark returns for quantile p of n non-null values of one partition: the sketch position
+    when the single-batch model applies (eps given, n < 50 000), else the exact rank max(1, ceil(p*n))."""
+    if eps is None or n >= GK_HEAD_SIZE or n <= 0:
+        return quantile_rank(p, n)
+    return gk_query_position(gk_single_batch_summary(n, eps), n, eps, p) + 1
+
+
+def approx_quantile_sorted(sorted_vals: np.ndarray, p: float, eps):
+    n = int(sorted_vals.size)
+    if n == 0:
+        return None
+    return sorted_vals[approx_quantile_rank(p, n, eps) - 1]
+
+
+SUMMARY_EPS = 1e-4       # Dataset.summary(): ApproximatePercentile accuracy 10000
+APPROX_QUANTILE_EPS = 0.01   # every approxQuantile(..., 0.01) call of the reference
+
 SUMMARY_PCTS = {"1%": 0.01, "5%": 0.05, "10%": 0.1, "25%": 0.25, "50%": 0.5,
                 "75%": 0.75, "90%": 0.9, "95%": 0.95, "99%": 0.99}
 
@@ -258,10 +336,14 @@ def equal_range_cutoffs(mn: float, mx: float, bin_size: int):
 
 
 def equal_frequency_cutoffs(sorted_x64: np.ndarray, bin_size: int):
-    """transformers.py:210-215: approxQuantile(cols, [j*(1/bin_size)], 0.01) restated
-    as the exact rank ceil(p*n) element (inside Spark's own error band)."""
+    """transformers.py:210-215: approxQuantile(cols, [j*(1/bin_size)], 0.01): the GK sketch position for one
+    partition of < 50 000 values, the exact rank ceil(p*n) element otherwise (inside Spark's own error band)."""
     w = 1 / bin_size
-    return [float(quantile_sorted(sorted_x64, j * w)) for j in range(1, bin_size)]
+    n = int(sorted_x64.size)
+    if n >= GK_HEAD_SIZE:
+        return [float(quantile_sorted(sorted_x64, j * w)) for j in range(1, bin_size)]
+    sm = gk_single_batch_summary(n, APPROX_QUANTILE_EPS)
+    return [float(sorted_x64[gk_query_position(sm, n, APPROX_QUANTILE_EPS, j * w)]) for j in range(1, bin_size)]
 
 
 def assign_bins(x64: np.ndarray, valid: np.ndarray, cutoffs, bin_size: int) -> np.ndarray:
