@@ -1,1 +1,2 @@
-from anovos_b200.data_analyzer.quality_checker import nullColumns_detection, IDness_detection, biasedness_detection  # noqa: F401
+from anovos_b200.data_analyzer.quality_checker import (  # noqa: F401
+    nullColumns_detection, outlier_detection, IDness_detection, biasedness_detection)

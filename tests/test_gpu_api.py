@@ -454,6 +454,59 @@ def test_quality_checker_consumers():
         qc.IDness_detection(None, t3, treatment="maybe")
 
 
+def test_outlier_detection(income_part0, tmp_path):
+    """data_analyzer/test_quality_checker.py:526-668 with unchanged inputs and expected values, plus product == oracle
+    (thresholds, counts and treated frames) on a seeded frame with nulls."""
+    import anovos.data_analyzer.quality_checker as qc
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    from test_oracle_golden import check_outlier_reference_tests
+
+    def view(odf):
+        def minmax(c):
+            m = engine.moments(odf, [c])[0]
+            return (m["min"], m["max"])
+        return {"rows": odf.count(), "columns": odf.columns, "minmax": minmax,
+                "nulls": lambda c: odf.count() - int(engine.moments(odf, [c])[0]["n_valid"])}
+
+    def run(table, print_impact=False, **kw):
+        r = qc.outlier_detection(None, table, print_impact=print_impact, **kw)
+        return (view(r[0]), r[1].toPandas()) if print_impact else view(r)
+
+    t = income_part0.append_column("label", pa.array([0] * income_part0.num_rows))
+    check_outlier_reference_tests(run, t, tmp_path)
+    # product vs oracle, every side / treatment, incl. a float32 column with NaN-free heavy tails and nulls
+    rng = np.random.default_rng(11)
+    n = 30_011
+    x = rng.standard_t(3, n).astype(np.float32)
+    y = rng.integers(0, 100, n).astype(np.int64)
+    z = np.where(rng.random(n) < 0.97, 0.0, rng.exponential(3.0, n))
+    tab = pa.table({"x": pa.array(x, mask=rng.random(n) < 0.1), "y": pa.array(y), "z": pa.array(z), "s": pa.array(["a"] * n)})
+    for side in ("upper", "lower", "both"):
+        for method in ("value_replacement", "null_replacement", "row_removal"):
+            exp_t, exp_p = O.outlier_detection(tab, detection_side=side, treatment_method=method)
+            got_t, got_p = qc.outlier_detection(None, tab, detection_side=side, treatment_method=method, print_impact=True)
+            gp = got_p.toPandas()
+            assert gp.values.tolist() == exp_p.values.tolist(), (side, method)
+            assert got_t.count() == exp_t.num_rows and got_t.columns == exp_t.column_names
+            for c in ("x", "y", "z"):
+                d, v = got_t.column(c).device()
+                e = exp_t.column(c).combine_chunks()
+                valid = np.asarray(e.is_valid())
+                g = d.cpu().numpy().astype(np.float64)
+                assert np.array_equal(g[valid], np.asarray(e.fill_null(0)).astype(np.float64)[valid]), (side, method, c)
+                gv = np.ones(len(g), bool) if v is None else ColumnFrame({c: got_t.column(c)}, got_t.count()).valid_mask(c).cpu().numpy()
+                assert np.array_equal(gv, valid), (side, method, c)
+    with pytest.raises(TypeError):
+        qc.outlier_detection(None, tab, list_of_cols=["s"])
+    with pytest.raises(TypeError):
+        qc.outlier_detection(None, tab, detection_side="sideways")
+    with pytest.raises(TypeError):
+        qc.outlier_detection(None, tab, detection_configs={"pctile_upper": 1.5})
+    with pytest.warns(UserWarning):
+        assert qc.outlier_detection(None, tab, treatment=False, print_impact=False).count() == n
+
+
 # ---- N3: IV / IG (data_analyzer/test_association_evaluator.py:25-240) ------------------------------------------
 
 def test_iv_ig(income_part0):

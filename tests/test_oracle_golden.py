@@ -369,8 +369,9 @@ IV_PINS = {"relationship": 1.6208, "marital-status": 1.3929, "occupation": 0.768
            "capital-gain": 0.3184, "sex": 0.3111, "workclass": 0.1686}
 IG_PINS = {"relationship": 0.1702, "marital-status": 0.1608, "occupation": 0.0916, "education": 0.0938, "education-num": 0.0887,
            "capital-gain": 0.0434, "sex": 0.0379, "workclass": 0.0223}
-# these two reference pins come out of approxQuantile(0.01) cutoffs (GK sketch): exact-rank cutoffs land within 10 %
-APPROX_PINS = {"age": (1.1891, 0.0944), "hours-per-week": (0.4441, 0.0549)}
+# these two reference pins come out of approxQuantile(0.01) cutoffs: reproduced by the GK single-batch rank rule
+# (spark_semantics.approx_quantile_rank); the textbook rank ceil(p*n) only lands within 10 % of them
+GK_PINS = {"age": (1.1891, 0.0944), "hours-per-week": (0.4441, 0.0549)}
 
 
 def label_table(income_part0):
@@ -385,8 +386,8 @@ def check_iv_ig(iv, ig):
         assert round(iv[a]["iv"], 4) == v, (a, iv[a]["iv"], v)
     for a, v in IG_PINS.items():
         assert round(ig[a]["ig"], 4) == v, (a, ig[a]["ig"], v)
-    for a, (v1, v2) in APPROX_PINS.items():
-        assert abs(iv[a]["iv"] - v1) < 0.1 * v1 and abs(ig[a]["ig"] - v2) < 0.1 * v2
+    for a, (v1, v2) in GK_PINS.items():
+        assert round(iv[a]["iv"], 4) == v1 and round(ig[a]["ig"], 4) == v2, (a, iv[a]["iv"], ig[a]["ig"])
 
 
 def test_iv_ig_known_answers(income_part0):
@@ -396,3 +397,92 @@ def test_iv_ig_known_answers(income_part0):
         O.IV_calculation(t, label_col="nope")
     with pytest.raises(TypeError):
         O.IV_calculation(t, event_label=7)
+
+
+# ---- N2: outlier_detection (data_analyzer/test_quality_checker.py:526-668) and the GK rank rule -------------------
+
+OUTLIER_PINS_UPPER = {"age": [0, 87, 0], "fnlwgt": [0, 518, 0], "logfnl": [0, 15, 0], "education-num": [0, 0, 0],
+                      "capital-gain": [0, 955, 0], "hours-per-week": [0, 515, 0], "capital-loss": [0, 0, 1]}   # :548-554
+
+
+def check_outlier_reference_tests(run, table, tmp_path):
+    """The reference's four outlier tests; `run(table, **kw)` -> (odf, odf_print pandas) hides oracle vs product."""
+    n_rows, n_cols = table.num_rows, len(table.column_names)
+    odf, pr = run(table, drop_cols=["ifa", "label"], treatment=True, treatment_method="row_removal", print_impact=True)   # :526-555
+    assert n_rows > odf["rows"] and odf["columns"] == table.column_names and pr.shape == (7, 4)
+    got = {r["attribute"]: [r["lower_outliers"], r["upper_outliers"], r["excluded_due_to_skewness"]] for r in pr.to_dict("records")}
+    assert got == OUTLIER_PINS_UPPER
+    odf, pr = run(table, list_of_cols=["age", "education-num"], detection_side="both",                                  # :558-592
+                  detection_configs={"pctile_lower": 0.02, "pctile_upper": 0.98}, treatment=True, output_mode="append",
+                  print_impact=True)
+    assert odf["rows"] == n_rows and len(odf["columns"]) == n_cols + 2
+    assert odf["minmax"]("age") == (17, 85) and odf["minmax"]("age_outliered") == (18, 66)
+    assert odf["minmax"]("education-num") == (1, 16) and odf["minmax"]("education-num_outliered") == (4, 15)
+    got = {r["attribute"]: [r["lower_outliers"], r["upper_outliers"], r["excluded_due_to_skewness"]] for r in pr.to_dict("records")}
+    assert got == {"age": [202, 482, 0], "education-num": [267, 205, 0]}
+    model = str(tmp_path / "outlier_model")                                                                              # :595-637
+    same = run(table, list_of_cols=["logfnl", "hours-per-week", "capital-loss"], detection_side="both", treatment=False,
+               model_path=model, print_impact=False)
+    assert same["rows"] == n_rows and same["columns"] == table.column_names
+    odf, pr = run(table, list_of_cols=["logfnl", "hours-per-week", "capital-gain", "capital-loss"], detection_side="lower",
+                  treatment=True, treatment_method="null_replacement", pre_existing_model=True, model_path=model,
+                  print_impact=True)
+    assert odf["rows"] == n_rows and odf["columns"] == table.column_names and pr.shape == (3, 4)
+    assert odf["nulls"]("hours-per-week") == table.column("hours-per-week").null_count + 825
+    assert odf["nulls"]("logfnl") == table.column("logfnl").null_count + 314
+    got = {r["attribute"]: [r["lower_outliers"], r["upper_outliers"], r["excluded_due_to_skewness"]] for r in pr.to_dict("records")}
+    assert got == {"hours-per-week": [825, 0, 0], "logfnl": [314, 0, 0], "capital-loss": [0, 0, 1]}
+    with pytest.raises(TypeError):                                                                                       # :640-656
+        run(table, list_of_cols=["capital-gain", "capital-loss"], detection_side="both",
+            detection_configs={"pctile_lower": 0.05, "stdev_lower": 3.0, "stdev_upper": 3.0}, treatment=True)
+    with pytest.raises(TypeError):                                                                                       # :658-668
+        run(table, list_of_cols=["capital-gain", "capital-loss"], detection_side="both",
+            detection_configs={"stdev_lower": 3.0, "stdev_upper": 3.0, "min_validation": 3}, treatment=True)
+
+
+def _oracle_outlier_run(tmp_models={}):
+    import pyarrow.compute as pc
+
+    def run(table, print_impact=False, model_path="NA", pre_existing_model=False, **kw):
+        params = None
+        cfg = kw.get("detection_configs")
+        if pre_existing_model:
+            kept, bounds, skewed = tmp_models[model_path]
+            cols = kw["list_of_cols"]
+            params = ([c for c in kept if c in cols], [b for c, b in zip(kept, bounds) if c in cols], [c for c in skewed if c in cols])
+        elif model_path != "NA":
+            cols = kw["list_of_cols"]
+            tmp_models[model_path] = O.outlier_bounds(table, cols, kw.get("detection_side", "upper"),
+                                                      O._DEFAULT_OUTLIER_CFG if cfg is None else cfg)
+        O.outlier_methodologies(kw.get("detection_side", "upper"), O._DEFAULT_OUTLIER_CFG if cfg is None else cfg)
+        odf, pr = O.outlier_detection(table, params=params, **kw)
+        view = {"rows": odf.num_rows, "columns": odf.column_names,
+                "minmax": lambda c: (pc.min(odf[c]).as_py(), pc.max(odf[c]).as_py()),
+                "nulls": lambda c: odf.column(c).null_count}
+        return (view, pr) if print_impact else view
+    return run
+
+
+def test_outlier_detection_known_answers(income_part0, tmp_path):
+    check_outlier_reference_tests(_oracle_outlier_run(), income_part0.append_column("label", pa.array([0] * income_part0.num_rows)),
+                                  tmp_path)
+
+
+def test_gk_rank_rule():
+    """Spark's sketch for one partition of < 50 000 values: data-independent positions.  Small n: no compression ->
+    the exact rank (median([23,42,51,55]) = 42, test_stats_generator.py:292-339); the product's closed form equals
+    the restated loop; beyond the head buffer the exact rule applies."""
+    from anovos_b200.shared import gk
+    assert S.approx_quantile_rank(0.5, 4, 1e-4) == 2 and S.approx_quantile_rank(0.5, 4, 0.01) == 2
+    for n in (1, 2, 3, 7, 49, 50, 51, 100, 101, 999, 5000, 5001, 6102, 16250, 32561, 49999):
+        for eps in (1e-4, 0.01, 0.05):
+            sm = S.gk_single_batch_summary(n, eps)
+            assert sm[0][0] == 0 and sm[-1][0] == n - 1 and sum(g for _, g, _ in sm) == n
+            for p in (0.0, 0.01, 0.02, 0.05, 0.1, 0.25, 3 * 0.1, 0.5, 7 * (1 / 10), 0.75, 0.95, 0.98, 0.99, 1.0):
+                r = S.gk_query_position(sm, n, eps, p) + 1
+                assert r == gk.spark_rank(n, p, eps), (n, eps, p)
+                assert abs(r - S.quantile_rank(p, n)) <= max(1, math.ceil(eps * n) + 1), (n, eps, p, r)   # inside Spark's band
+                if 2 * eps * n <= 1:
+                    assert r == S.quantile_rank(p, n)
+    assert gk.spark_rank(50000, 0.5, 0.01) == 25000 and gk.spark_rank(0, 0.5, 0.01) == 0
+    assert S.approx_quantile_rank(0.5, 60000, 0.01) == 30000
