@@ -11,6 +11,7 @@ Follows (relative to /root/reference/src/main/anovos):
 """
 from __future__ import annotations
 
+import json
 import math
 import os
 import warnings
@@ -22,6 +23,14 @@ import pyarrow as pa
 from . import spark_semantics as S
 
 R = S.round_half_up
+
+
+def with_spark_partitions(table: pa.Table, rows_per_partition) -> pa.Table:
+    """Tag a table with the way Spark partitioned it (rows per partition, in order): percentiles then follow the
+    per-partition Greenwald-Khanna sketches merged in partition order, like Dataset.summary() / approxQuantile."""
+    md = dict(table.schema.metadata or {})
+    md[b"spark_partition_rows"] = json.dumps([int(k) for k in rows_per_partition]).encode()
+    return table.replace_schema_metadata(md)
 
 
 def table_from_rows(rows, names) -> pa.Table:
@@ -87,6 +96,11 @@ class ColumnProfile:
         self.is_num = self.sdtype in ("double", "int", "bigint", "float", "long") or self.sdtype.startswith("decimal")
         self._x64 = None
         self._sorted = None
+        self._sketch = {}
+        md = table.schema.metadata or {}
+        self.partition_rows = json.loads(md[b"spark_partition_rows"]) if b"spark_partition_rows" in md else None
+        if self.partition_rows is not None and sum(self.partition_rows) != self.N:
+            raise ValueError("spark_partition_rows does not add up to the table's rows")
 
     @property
     def x64(self):
@@ -117,11 +131,30 @@ class ColumnProfile:
             return (float(nn.min()) if nn.size else float("nan")), float("nan")
         return float(x.min()), float(x.max())
 
+    def _partition_values(self):
+        """Non-null float64 values of each Spark partition (schema metadata `spark_partition_rows`), arrival order."""
+        out, r0 = [], 0
+        for k in self.partition_rows:
+            sel = slice(r0, r0 + k)
+            out.append(self.values[sel][self.valid[sel]].astype(np.float64))
+            r0 += k
+        return out
+
     def quantile(self, p, eps=S.SUMMARY_EPS):
         """summary() percentile (eps 1e-4) or approxQuantile(..., eps): Spark's sketch position for one partition
         of < 50 000 values, the exact rank otherwise (S.approx_quantile_rank)."""
         if self.n == 0:
             return None
+        if self.partition_rows is not None and eps is not None:    # the full sketch: per partition, merged in order
+            key = ("parts", eps)
+            if key not in self._sketch:
+                samples, n = [], 0
+                for part in self._partition_values():
+                    s_, c_ = S.gk_sketch(part, eps)
+                    samples, n = S.gk_merge(samples, n, s_, c_, eps)
+                self._sketch[key] = (samples, n)
+            samples, n = self._sketch[key]
+            return float(S.gk_query_value(samples, n, eps, p))
         key = (self.n, eps)
         if key not in _GK_CACHE:
             _GK_CACHE[key] = S.gk_single_batch_summary(self.n, eps) if (eps is not None and self.n < S.GK_HEAD_SIZE) else None

@@ -296,6 +296,111 @@ def gk_query_position(summary, n: int, eps: float, p: float) -> int:
     return summary[-1][0]
 
 
+# --- the full sketch (arrival order, several partitions): what Dataset.summary() / approxQuantile return in general.
+# Pinned by the 81 stored summary() percentiles of the reference notebook on the income CSV, which Spark read as TWO
+# partitions (Hadoop split of the 5.9 MB file at 4 MiB = spark.sql.files.openCostInBytes): tests/test_oracle_golden.py.
+
+GK_COMPRESS_THRESHOLD = 10000
+
+
+def gk_compress(samples, merge_threshold):
+    """QuantileSummaries.compressImmut on a list of (value, g, delta)."""
+    if not samples:
+        return []
+    res = []
+    head = list(samples[-1])
+    for i in range(len(samples) - 2, 0, -1):
+        v, g, d = samples[i]
+        if g + head[1] + head[2] < merge_threshold:
+            head[1] += g
+        else:
+            res.append(tuple(head))
+            head = [v, g, d]
+    res.append(tuple(head))
+    if samples[0][0] <= head[0] and len(samples) > 1:
+        res.append(tuple(samples[0]))
+    res.reverse()
+    return res
+
+
+def gk_insert_batch(samples, count, batch_sorted, eps):
+    """withHeadBufferInserted: merge one sorted head buffer into the sample list -> (samples, count)."""
+    out, si, cur = [], 0, count
+    m = len(batch_sorted)
+    for oi, x in enumerate(batch_sorted):
+        while si < len(samples) and samples[si][0] <= x:
+            out.append(samples[si])
+            si += 1
+        cur += 1
+        first_or_last = (not out) or (si == len(samples) and oi == m - 1)
+        out.append((float(x), 1, 0 if first_or_last else int(math.floor(2 * eps * cur))))
+    out.extend(samples[si:])
+    return out, cur
+
+
+def gk_sketch(values, eps):
+    """One partition: values in ARRIVAL order -> (compressed samples, count), flushing the head buffer every 50 000
+    insertions (and compressing when >= 10 000 samples are held) exactly like QuantileSummaries.insert, then the
+    final compress()."""
+    samples, count = [], 0
+    vals = np.asarray(values, dtype=np.float64)
+    for b0 in range(0, len(vals), GK_HEAD_SIZE):
+        batch = np.sort(vals[b0:b0 + GK_HEAD_SIZE], kind="stable")
+        full = len(batch) == GK_HEAD_SIZE
+        samples, count = gk_insert_batch(samples, count, batch.tolist(), eps)
+        if full and len(samples) >= GK_COMPRESS_THRESHOLD:
+            samples = gk_compress(samples, 2 * eps * count)
+    return gk_compress(samples, 2 * eps * count), count
+
+
+def gk_merge(a, na, b, nb, eps):
+    """QuantileSummaries.merge (Spark >= 3.0: deltas of interleaved samples grow by the other side's 2*eps*count)."""
+    if nb == 0:
+        return list(a), na
+    if na == 0:
+        return list(b), nb
+    add_self, add_other = int(math.floor(2 * eps * nb)), int(math.floor(2 * eps * na))
+    out, i, j = [], 0, 0
+    while i < len(a) and j < len(b):
+        if a[i][0] < b[j][0]:
+            s, ad = a[i], (add_self if j > 0 else 0)
+            i += 1
+        else:
+            s, ad = b[j], (add_other if i > 0 else 0)
+            j += 1
+        out.append((s[0], s[1], s[2] + ad))
+    out.extend(a[i:])
+    out.extend(b[j:])
+    return gk_compress(out, 2 * eps * (na + nb)), na + nb
+
+
+def gk_query_value(samples, n, eps, p):
+    if not samples:
+        return None
+    if p <= eps:
+        return samples[0][0]
+    if p >= 1 - eps:
+        return samples[-1][0]
+    target_error = max(g + d for _, g, d in samples) / 2.0
+    rank = int(math.ceil(p * n))
+    min_rank, i = samples[0][1], 0
+    while i < len(samples) - 1:
+        if min_rank + samples[i][2] - target_error <= rank <= min_rank + target_error:
+            return samples[i][0]
+        i += 1
+        min_rank += samples[i][1]
+    return samples[-1][0]
+
+
+def gk_partitioned_quantiles(partitions, probs, eps):
+    """partitions: list of value arrays (non-null, arrival order), merged in partition order -> list of quantiles."""
+    samples, n = [], 0
+    for part in partitions:
+        s, c = gk_sketch(part, eps)
+        samples, n = gk_merge(samples, n, s, c, eps)
+    return [gk_query_value(samples, n, eps, p) for p in probs]
+
+
 def approx_quantile_rank(p: float, n: int, eps) -> int:
     """1-based rank Spark returns for quantile p of n non-null values of one partition: the sketch position
     when the single-batch model applies (eps given, n < 50 000), else the exact rank max(1, ceil(p*n))."""

@@ -12,6 +12,8 @@ reference stores in its notebooks, plus the input datasets they were computed on
   income_part1.parquet    data/test_dataset/part-00001-*.snappy.parquet (test_transformers.py:22)
   income_part0.parquet    data/test_dataset/part-00000-*.snappy.parquet (test_association_evaluator.py:17)
   stability.parquet       examples/data/income_dataset/stability_index/{0..11} stacked, column `_ds` = dataset id
+  income_partitions.json  how Spark split the income CSV when the notebooks ran: Hadoop line splits of the 5.9 MB file at
+                          spark.sql.files.openCostInBytes = 4 MiB (any local[*] with >= 3 cores) -> rows per partition
   notebook_stats.json     stored outputs of examples/notebooks/data_analyzer__stats_generator.ipynb
   notebook_drift.json     stored outputs of examples/notebooks/drift_stability.ipynb
 """
@@ -91,6 +93,26 @@ def notebook_tables(path):
     return out
 
 
+def csv_partition_rows(path, split_bytes=4 * 1024 * 1024):
+    """Rows per Spark partition of a single CSV: FilePartition cuts the file every maxSplitBytes = max(openCostInBytes,
+    min(maxPartitionBytes, totalBytes / cores)) = 4 MiB here; Hadoop's LineRecordReader gives a split every line that
+    STARTS at an offset <= its end (and skips its own first, partial line)."""
+    raw = open(path, "rb").read()
+    starts, pos = [], 0
+    for line in raw.split(b"\n")[:-1] if raw.endswith(b"\n") else raw.split(b"\n"):
+        starts.append(pos)
+        pos += len(line) + 1
+    starts = starts[1:]                                   # header line
+    rows, end = [], split_bytes
+    while True:
+        k = sum(1 for s_ in starts if s_ <= end) - sum(rows)
+        rows.append(k)
+        if end >= len(raw):
+            break
+        end += split_bytes
+    return {"file_bytes": len(raw), "split_bytes": split_bytes, "rows_per_partition": [r for r in rows if r]}
+
+
 def main():
     inc = read_income(REF + "/examples/data/income_dataset/csv/part-00000-8beb3930-8a44-4b7b-906b-a6deca466d9f-c000.csv")
     pq.write_table(inc, OUT + "/income.parquet", compression="zstd")
@@ -113,6 +135,8 @@ def main():
               open(OUT + "/notebook_stats.json", "w"), indent=0)
     json.dump(notebook_tables(REF + "/examples/notebooks/drift_stability.ipynb"),
               open(OUT + "/notebook_drift.json", "w"), indent=0)
+    json.dump(csv_partition_rows(REF + "/examples/data/income_dataset/csv/part-00000-8beb3930-8a44-4b7b-906b-a6deca466d9f-c000.csv"),
+              open(OUT + "/income_partitions.json", "w"))
     print(inc.schema, inc.num_rows, src.num_rows)
 
 

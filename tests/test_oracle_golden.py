@@ -486,3 +486,18 @@ def test_gk_rank_rule():
                     assert r == S.quantile_rank(p, n)
     assert gk.spark_rank(50000, 0.5, 0.01) == 25000 and gk.spark_rank(0, 0.5, 0.01) == 0
     assert S.approx_quantile_rank(0.5, 60000, 0.01) == 30000
+
+
+def test_nb_percentiles_exact_with_spark_partitions(income, nb_stats):
+    """With the partitioning Spark used for the notebook run (two Hadoop splits of the CSV at 4 MiB,
+    tests/golden/income_partitions.json) the restated sketch - one sorted batch per partition, compress, merge in
+    partition order, query - reproduces ALL 81 stored summary() percentiles, every median and every IQR."""
+    import json
+    import os
+    from conftest import GOLDEN
+    parts = json.load(open(os.path.join(GOLDEN, "income_partitions.json")))["rows_per_partition"]
+    assert sum(parts) == income.num_rows and len(parts) == 2
+    t = O.with_spark_partitions(income, parts)
+    _check_table(O.measures_of_percentiles(t), nb_stats[35], ["min"] + list(S.SUMMARY_PCTS) + ["max"])
+    _check_table(O.measures_of_centralTendency(t), nb_stats[17], ["mean", "median", "mode_rows", "mode_pct"])
+    _check_table(O.measures_of_dispersion(t), nb_stats[31], ["stddev", "variance", "cov", "IQR", "range"])
