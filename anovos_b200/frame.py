@@ -408,6 +408,11 @@ def as_frame(idf) -> ColumnFrame:
         return idf
     mod = type(idf).__module__
     if mod.startswith("pyarrow"):
+        md = idf.schema.metadata or {}
+        if b"spark_partition_rows" in md:   # the table says how Spark partitioned it: percentiles follow Spark's sketch
+            import json
+            from .partitioned import PartitionedFrame
+            return PartitionedFrame.from_arrow_partitions(idf, json.loads(md[b"spark_partition_rows"]))
         return ColumnFrame.from_arrow(idf)
     if mod.startswith("pandas"):
         return ColumnFrame.from_pandas(idf)

@@ -113,6 +113,8 @@ class PartitionedFrame:
 
     is_partitioned = True
 
+    spark_partitions = False   # True: the chunks ARE the partitions Spark would scan (see gk_quantiles)
+
     def __init__(self, schema: ColumnFrame, chunk_rows, chunk_fn, group=None, release=True):
         self._schema = schema
         self.chunk_rows = [int(r) for r in chunk_rows]
@@ -143,6 +145,30 @@ class PartitionedFrame:
         starts = list(range(0, fr.n_rows, chunk_rows)) or [0]
         return PartitionedFrame(fr.slice_rows(0, 0), [min(chunk_rows, fr.n_rows - s) for s in starts],
                                 lambda i: fr.slice_rows(starts[i], starts[i] + chunk_rows), group=group)
+
+    @staticmethod
+    def from_arrow_partitions(table, rows_per_partition, spark=True) -> "PartitionedFrame":
+        """A pyarrow table cut into the row ranges Spark scanned as partitions (in order).  String columns are
+        dictionary-encoded once so that every partition shares the dictionary."""
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        rows = [int(k) for k in rows_per_partition]
+        if sum(rows) != table.num_rows:
+            raise ValueError("rows_per_partition does not add up to the table's rows")
+        cols = []
+        for f in table.schema:
+            c = table.column(f.name)
+            if pa.types.is_string(f.type) or pa.types.is_large_string(f.type):
+                c = pc.dictionary_encode(c.combine_chunks())
+            cols.append(c)
+        table = pa.table(cols, names=table.column_names)
+        frames, r0 = [], 0
+        for k in rows:
+            frames.append(ColumnFrame.from_arrow(table.slice(r0, k)))
+            r0 += k
+        out = PartitionedFrame(frames[0], rows, lambda i: frames[i], release=True)
+        out.spark_partitions = bool(spark)
+        return out
 
     # ---- Spark-DataFrame-like surface -----------------------------------------------------------
     @property
@@ -324,11 +350,72 @@ class PartitionedFrame:
         raise NotImplementedError("bin ids of a row-partitioned frame are produced per chunk: use attribute_binning(), "
                                   "which returns a PartitionedFrame")
 
+    def gk_quantiles(self, names, probs, eps):
+        """Spark-partitioned frames (`spark_partitions=True`: every chunk is one Spark partition, in order): the
+        quantiles Dataset.summary() / approxQuantile return - one Greenwald-Khanna sketch per partition, merged in
+        partition order (shared/gk.py).  The sketch keeps the order statistics at data-independent positions, so the
+        sort kernel supplies them per partition and only those few thousand samples are merged on the host.
+        -> dict name -> [value | None per prob], or None when a partition holds >= 50 000 non-null values of some
+        column (Spark then flushes its head buffer mid-partition: arrival-order dependent, not emulated)."""
+        from . import engine
+        from .shared import gk
+        names = [n for n in names]
+        sketch = {n: ([], 0) for n in names}
+        for ch in self.chunks(names):
+            mom = engine.moments(ch, names)
+            nv = [int(m["n_valid"]) for m in mom]
+            if any(k >= gk.HEAD_SIZE for k in nv):
+                return None
+            pos = [gk.sample_positions(k, eps) for k in nv]
+            width = max((len(q) for q in pos), default=0)
+            if width == 0:
+                continue
+            rk = np.zeros((len(names), width), np.int64)
+            for i, q in enumerate(pos):
+                rk[i, :len(q)] = q + 1
+            _, vals = engine.sort_mode_distinct(ch, names, rk)
+            for i, n in enumerate(names):
+                s = gk.partition_samples(vals[i, :len(pos[i])], nv[i], eps)
+                sketch[n] = gk.merge_samples(sketch[n][0], sketch[n][1], s, nv[i], eps)
+        return {n: [gk.query_samples(sketch[n][0], sketch[n][1], eps, p) for p in probs] for n in names}
+
+    def materialize(self, names=None) -> ColumnFrame:
+        """Concatenate the local chunks of `names` into one device-resident ColumnFrame (for the passes that need
+        whole columns - the exact mode / distinct count sort).  Only sensible when the columns fit in HBM."""
+        torch = _lib.require_cuda()
+        from .frame import Column, pack_bits_device
+        names = [n for n in (names or self.columns) if self.column(n).kind != "other"]
+        data = {n: [] for n in names}
+        valid = {n: [] for n in names}
+        any_null = {n: False for n in names}
+        for ch in self.chunks(names):
+            for n in names:
+                d, v = ch.column(n).device()
+                data[n].append(d)
+                valid[n].append(ch.valid_mask(n))
+                any_null[n] |= v is not None
+        out = OrderedDict()
+        for n in names:
+            c = self.column(n)
+            d = torch.cat(data[n]) if data[n] else torch.empty(0, device="cuda")
+            v = pack_bits_device(torch.cat(valid[n])) if any_null[n] else None
+            out[n] = Column(n, c.sdtype, self.n_rows_local, dev=d, dev_valid=v, anv_dtype=c.anv_dtype, dictionary=c.dictionary)
+        return ColumnFrame(out, self.n_rows_local)
+
     def sort_mode_distinct(self, names, ranks=None):
-        raise NotImplementedError(
-            "exact mode / exact distinct count of numeric columns needs a global group-by, which row partitions "
-            "cannot merge: call partitioned.repartition_to_columns(frame) first (all-to-all, each rank then owns "
-            "whole columns), or use the approximate distinct count (HLL++)")
+        """Exact mode / distinct count of numeric columns needs whole columns.  Local chunks are concatenated on the
+        device when they fit (a chunked host table, a Spark-partitioned table); row slabs on several ranks must be
+        exchanged first (repartition_to_columns)."""
+        from . import engine
+        torch = _lib.require_cuda()
+        names = list(names)
+        need = sum(self.n_rows_local * (8 if self.column(n).anv_dtype in (_lib.ANV_F64, _lib.ANV_I64) else 4) for n in names)
+        if self.group is not None or 3 * need > torch.cuda.mem_get_info()[0]:
+            raise NotImplementedError(
+                "exact mode / exact distinct count of numeric columns needs a global group-by, which row partitions "
+                "cannot merge: call partitioned.repartition_to_columns(frame) first (all-to-all, each rank then owns "
+                "whole columns), or use the approximate distinct count (HLL++)")
+        return engine.sort_mode_distinct(self.materialize(names), names, ranks)
 
 
 # ---- row slabs -> column blocks (the one real exchange step) ---------------------------------------

@@ -42,6 +42,19 @@ def n_valid(frame: ColumnFrame, names):
 def quantiles(frame: ColumnFrame, names, probs, eps=SUMMARY_EPS):
     """dict name -> list of order statistics (None if empty) at the ranks Spark returns for `probs`: eps is the
     relativeError of the replaced call (summary(): 1e-4, approxQuantile(..., 0.01): 0.01), see shared/gk.py."""
+    if getattr(frame, "spark_partitions", False) and eps is not None:
+        gc = _cache(frame, ("gk_quantiles", eps))
+        # resolve the nine summary() percentiles together with the request: one sort per partition serves them all
+        ask = list(dict.fromkeys(list(probs) + (SUMMARY_PROBS if eps == SUMMARY_EPS else [])))
+        todo = [n for n in names if any((n, p) not in gc for p in probs)]
+        if todo:
+            res = frame.gk_quantiles(todo, ask, eps)
+            if res is not None:
+                for n in todo:
+                    for p, v in zip(ask, res[n]):
+                        gc[(n, p)] = v
+        if all((n, p) in gc for n in names for p in probs):
+            return {n: [gc[(n, p)] for p in probs] for n in names}
     c = _cache(frame, "quantiles")
     mom = moments(frame, names)
     want, extra = {}, {}

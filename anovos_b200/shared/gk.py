@@ -80,3 +80,89 @@ def spark_rank(n: int, p: float, eps) -> int:
 
 def spark_ranks(n: int, probs, eps):
     return [spark_rank(n, p, eps) for p in probs]
+
+
+# ---- several partitions: the sketches are merged in partition order (host arithmetic on a few thousand samples) ------
+# A partition of fewer than 50 000 non-null values contributes the samples at the data-independent positions of
+# `_summary`; their VALUES come from the sort kernel (order statistics of the partition).  Merging is value-dependent
+# (QuantileSummaries.merge interleaves the two sample lists), so it happens here, on the host, on the samples only.
+
+def partition_samples(values_at_positions, n: int, eps: float):
+    """-> [(value, g, delta)] of one partition's compressed sketch; values_at_positions[i] = the order statistic at
+    position sample_positions(n, eps)[i]."""
+    if n <= 0:
+        return []
+    pos, min_rank, max_rank, _ = _summary(int(n), float(eps))
+    g = np.diff(np.concatenate([[0], min_rank]))
+    return list(zip([float(v) for v in values_at_positions], g.tolist(), (max_rank - min_rank).tolist()))
+
+
+def sample_positions(n: int, eps: float):
+    """0-based positions (in the partition's sorted non-null values) of the samples its sketch keeps."""
+    if n <= 0:
+        return np.zeros(0, np.int64)
+    if n == 1:
+        return np.zeros(1, np.int64)
+    return _summary(int(n), float(eps))[0]
+
+
+def _compress(samples, thr):
+    if not samples:
+        return []
+    res = []
+    hv, hg, hd = samples[-1]
+    for i in range(len(samples) - 2, 0, -1):
+        v, g, d = samples[i]
+        if g + hg + hd < thr:
+            hg += g
+        else:
+            res.append((hv, hg, hd))
+            hv, hg, hd = v, g, d
+    res.append((hv, hg, hd))
+    if samples[0][0] <= hv and len(samples) > 1:
+        res.append(samples[0])
+    res.reverse()
+    return res
+
+
+def merge_samples(a, na: int, b, nb: int, eps: float):
+    """QuantileSummaries.merge (Spark >= 3.0) of two compressed sketches -> (samples, count)."""
+    if nb == 0:
+        return list(a), na
+    if na == 0:
+        return list(b), nb
+    add_a, add_b = int(math.floor(2 * eps * nb)), int(math.floor(2 * eps * na))
+    out, i, j = [], 0, 0
+    la, lb = len(a), len(b)
+    while i < la and j < lb:
+        if a[i][0] < b[j][0]:
+            v, g, d = a[i]
+            d += add_a if j > 0 else 0
+            i += 1
+        else:
+            v, g, d = b[j]
+            d += add_b if i > 0 else 0
+            j += 1
+        out.append((v, g, d))
+    out.extend(a[i:])
+    out.extend(b[j:])
+    return _compress(out, 2 * eps * (na + nb)), na + nb
+
+
+def query_samples(samples, n: int, eps: float, p: float):
+    if not samples:
+        return None
+    if p <= eps:
+        return samples[0][0]
+    if p >= 1 - eps:
+        return samples[-1][0]
+    te = max(g + d for _, g, d in samples) / 2.0
+    rank = int(math.ceil(p * n))
+    min_rank, i = samples[0][1], 0
+    last = len(samples) - 1
+    while i < last:
+        if min_rank + samples[i][2] - te <= rank <= min_rank + te:
+            return samples[i][0]
+        i += 1
+        min_rank += samples[i][1]
+    return samples[-1][0]

@@ -225,8 +225,10 @@ def test_attribute_binning(tr, income_part1, tmp_path):
 
 # ---- (2) notebook golden vectors through the product API -----------------------------------------------
 
-def _check(df, t, cols, skip=()):
+def _check(df, t, cols, skip=(), only_present=False):
     got, exp = frame_by_attr(df.toPandas()), table_by_attr(t)
+    if only_present:
+        exp = {a: r for a, r in exp.items() if a in got}
     assert set(got) == set(exp)
     bad = [(a, c, got[a][c], row[c]) for a, row in exp.items() for c in cols
            if (a, c) not in skip and not shown_close(None if pd.isna(got[a][c]) else got[a][c], row[c])]
@@ -268,6 +270,27 @@ def test_nb_percentiles_equal_oracle(sg, income):
     exp = O.measures_of_percentiles(income)
     assert got["attribute"].tolist() == exp["attribute"].tolist()
     assert np.array_equal(got.drop(columns="attribute").values.astype(float), exp.drop(columns="attribute").values.astype(float))
+
+
+def test_nb_percentiles_exact_with_spark_partitions(sg, income, nb_stats):
+    """The table tagged with Spark's partitioning of the notebook run (tests/golden/income_partitions.json): the product
+    takes the per-partition sketch samples from the sort kernel, merges them like QuantileSummaries and reproduces
+    ALL 81 stored summary() percentiles, every median and every IQR - and every other statistic as before."""
+    import json
+    from conftest import GOLDEN
+    parts = json.load(open(os.path.join(GOLDEN, "income_partitions.json")))["rows_per_partition"]
+    t = O.with_spark_partitions(income, parts)
+    _check(sg.measures_of_percentiles(None, t), nb_stats[35], ["min"] + list(S.SUMMARY_PCTS) + ["max"])
+    _check(sg.measures_of_centralTendency(None, t), nb_stats[17], ["mean", "median", "mode_rows", "mode_pct"])
+    _check(sg.measures_of_dispersion(None, t), nb_stats[31], ["stddev", "variance", "cov", "IQR", "range"])
+    _check(sg.measures_of_counts(None, t), nb_stats[11], ["fill_count", "missing_count", "nonzero_count"])
+    _check(sg.measures_of_shape(None, t), nb_stats[39], ["skewness", "kurtosis"])
+    _check(sg.measures_of_cardinality(None, t), nb_stats[23], ["unique_values", "IDness"])
+    ora = frame_by_attr(O.measures_of_percentiles(t))
+    got = frame_by_attr(sg.measures_of_percentiles(None, t).toPandas())
+    for a in got:   # and identical to the oracle's full sketch, value for value
+        for c in S.SUMMARY_PCTS:
+            assert (pd.isna(got[a][c]) and ora[a][c] is None) or got[a][c] == ora[a][c], (a, c)
 
 
 def test_nb_drift(dd, income, income_source, nb_drift, tmp_path):

@@ -84,9 +84,11 @@ def _check_against_whole(whole, parts, tmp_path, exact_mode=False):
     if cat:  # the mode of string columns merges (code histograms add)
         a, b = sg.mode_computation(None, whole, cat).toPandas(), sg.mode_computation(None, parts, cat).toPandas()
         assert a.equals(b)
-    if not exact_mode:
-        with pytest.raises(NotImplementedError):
-            sg.mode_computation(None, parts, num[:1])
+    # numeric mode / exact distinct need whole columns: local chunks are concatenated on the device when they fit
+    a, b = sg.measures_of_centralTendency(None, whole).toPandas(), sg.measures_of_centralTendency(None, parts).toPandas()
+    _same_table(a, b)
+    a, b = sg.uniqueCount_computation(None, whole).toPandas(), sg.uniqueCount_computation(None, parts).toPandas()
+    _same_table(a, b)
     # binning: the chunks of the binned frame are the row slices of the resident result
     for method in ("equal_range", "equal_frequency"):
         bw = tr.attribute_binning(None, whole, num, method_type=method, bin_size=7)
@@ -191,6 +193,11 @@ def _rank_worker(rank, world, port, ret):
     out = {"count": parts.count(), "mom": engine.moments(parts, slab.columns).tolist()}
     for fn in ("measures_of_counts", "measures_of_percentiles", "measures_of_cardinality", "measures_of_shape"):
         out[fn] = getattr(sg, fn)(None, parts).toPandas().to_dict("list")
+    try:   # row slabs on several ranks cannot merge a numeric mode: the caller must exchange first
+        sg.mode_computation(None, parts, num[:1])
+        out["mode_error"] = False
+    except NotImplementedError:
+        out["mode_error"] = True
     out["drift"] = dd.statistics(None, tparts, parts, method_type="all", use_sampling=False,
                                  source_path="/tmp/anv_part_test_%d_%d" % (port, rank)).toPandas().to_dict("list")
     # (b) the exchange: row slabs -> whole columns of this rank's block, then the full column path (incl. exact mode)
@@ -216,7 +223,7 @@ def test_two_ranks_row_slabs_match_single_frame(tmp_path):
     for k in ("count", "mom", "measures_of_counts", "measures_of_percentiles", "measures_of_cardinality",
               "measures_of_shape", "drift"):
         assert repr(a[k]) == repr(b[k]), k                      # every rank takes the same decisions
-    assert a["count"] == ROWS
+    assert a["count"] == ROWS and a["mode_error"] and b["mode_error"]
     mw = engine.moments(whole, whole.columns)
     mp_ = np.array([tuple(r) for r in a["mom"]], dtype=engine._MOM_DT)
     for f in ("n_valid", "n_nonzero", "min", "max"):
