@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import os
 
+import numpy as np
+
 from ..frame import ColumnFrame, as_frame
 from ..result import ResultFrame
 
@@ -25,14 +27,60 @@ def _part_files(path, ext):
     return [path]
 
 
+OPEN_COST = 4 * 1024 * 1024          # spark.sql.files.openCostInBytes
+MAX_PARTITION = 128 * 1024 * 1024    # spark.sql.files.maxPartitionBytes
+
+
+def spark_file_partitions(files, cores):
+    """How Spark (FilePartition.getFilePartitions, local[cores]) cuts `files` into scan partitions:
+    maxSplitBytes = min(maxPartitionBytes, max(openCostInBytes, sum(len + openCost) / cores)); files by size
+    descending, each cut every maxSplitBytes, the pieces packed next-fit.  -> [[(path, start, length), ...], ...]"""
+    sized = sorted(((os.path.getsize(f), f) for f in files), key=lambda t: -t[0])
+    total = sum(n + OPEN_COST for n, _ in sized)
+    max_split = min(MAX_PARTITION, max(OPEN_COST, total // max(int(cores), 1)))
+    pieces = [(f, off, min(max_split, n - off)) for n, f in sized for off in range(0, max(n, 1), max_split)]
+    parts, cur, size = [], [], 0
+    for p in pieces:
+        if cur and size + p[2] > max_split:
+            parts.append(cur)
+            cur, size = [], 0
+        cur.append(p)
+        size += p[2] + OPEN_COST
+    if cur:
+        parts.append(cur)
+    return parts
+
+
+def csv_rows_in_range(path, start, length, header):
+    """Rows Hadoop's LineRecordReader hands to the split [start, start+length): every line that STARTS at an offset
+    <= the split's end, minus the lines of earlier splits (a split with start > 0 skips its first, partial line)."""
+    raw = open(path, "rb").read()
+    starts = np.flatnonzero(np.frombuffer(raw, np.uint8) == 10) + 1
+    starts = np.concatenate([[0], starts[starts < len(raw)]])
+    if header:
+        starts = starts[1:]
+
+    def upto(end):      # lines starting at an offset <= end
+        return int(np.searchsorted(starts, end, "right"))
+    lo = 0 if start == 0 else upto(start)
+    return upto(start + length) - lo if start + length < len(raw) else len(starts) - lo
+
+
 def read_dataset(spark, file_path, file_type, file_configs={}):
     """-> ColumnFrame.  csv options honoured: header, delimiter / sep, inferSchema (without it every column is
-    a string, like Spark), nullValue; empty fields are nulls (Spark's default)."""
+    a string, like Spark), nullValue; empty fields are nulls (Spark's default).
+    Extra option `spark_cores` (N of the `local[N]` being replaced): the frame is returned as the scan partitions
+    Spark would create for these files (PartitionedFrame, rows in Spark's partition order), so that summary() /
+    approxQuantile percentiles come out exactly as Spark's per-partition sketches would give them."""
     import pyarrow as pa
     import pyarrow.csv as pacsv
     import pyarrow.parquet as pq
+    cores = {k.lower(): v for k, v in file_configs.items()}.get("spark_cores")
+    per_file = {}
     if file_type == "parquet":
-        t = pa.concat_tables([pq.read_table(f) for f in _part_files(file_path, "parquet")], promote_options="default")
+        for f in _part_files(file_path, "parquet"):
+            per_file[f] = pq.read_table(f)
+        t = pa.concat_tables(list(per_file.values()), promote_options="default")
     elif file_type == "csv":
         cfg = {k.lower(): v for k, v in file_configs.items()}
         header = _truthy(cfg.get("header", "false"))
@@ -54,6 +102,7 @@ def read_dataset(spark, file_path, file_type, file_configs={}):
             if not header:
                 tb = tb.rename_columns(["_c%d" % i for i in range(tb.num_columns)])   # Spark's default names
             tables.append(tb)
+            per_file[f] = tb
         t = pa.concat_tables(tables, promote_options="default")
         if infer:  # Spark infers IntegerType for integers that fit 32 bits and StringType for all-null columns
             import pyarrow.compute as pc
@@ -68,7 +117,39 @@ def read_dataset(spark, file_path, file_type, file_configs={}):
                         t = t.set_column(i, fld.name, t.column(i).cast(pa.int32()))
     else:
         raise NotImplementedError("file_type %r: only csv and parquet are part of the B200 hot-path build" % file_type)
+    if cores:
+        return _as_spark_partitions(t, per_file, int(cores), file_type, file_type == "csv" and header)
     return ColumnFrame.from_arrow(t)
+
+
+def _as_spark_partitions(t, per_file, cores, file_type, header):
+    """Re-order the rows into Spark's scan-partition order and tag the partition sizes."""
+    import pyarrow as pa
+    from ..partitioned import PartitionedFrame
+    files = list(per_file)
+    first_row, r = {}, 0
+    for f in files:                                   # rows of file f inside t (typed like t)
+        first_row[f] = r
+        r += per_file[f].num_rows
+    consumed = {f: 0 for f in files}
+    slices, rows = [], []
+    for part in spark_file_partitions(files, cores):
+        k_part = 0
+        for f, start, length in part:
+            if file_type == "csv":
+                k = csv_rows_in_range(f, start, length, header)
+            elif start == 0 and length >= os.path.getsize(f):
+                k = per_file[f].num_rows
+            else:
+                raise NotImplementedError("spark_cores: parquet files larger than one split are not supported")
+            slices.append(t.slice(first_row[f] + consumed[f], k))
+            consumed[f] += k
+            k_part += k
+        rows.append(k_part)
+    if any(consumed[f] != per_file[f].num_rows for f in files):
+        raise ValueError("spark_cores: split arithmetic does not cover every row (quoted newlines are not supported)")
+    keep = [k for k in rows if k]
+    return PartitionedFrame.from_arrow_partitions(pa.concat_tables(slices), keep if keep else [0])
 
 
 def write_dataset(idf, file_path, file_type, file_configs={}, column_order=[]):

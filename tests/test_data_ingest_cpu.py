@@ -41,3 +41,40 @@ def test_read_csv_and_parquet_typing(tmp_path, income):
         write_dataset(df, str(out), "csv", {"header": "True"})
     with pytest.raises(ValueError):
         write_dataset(df, str(tmp_path / "o2"), "csv", column_order=["mean"])
+
+
+def test_spark_scan_partitions(tmp_path):
+    """FilePartition arithmetic (maxSplitBytes, size-descending files, next-fit packing) and Hadoop's line-split rule:
+    the income CSV of the reference (5 891 566 bytes) splits at 4 MiB for local[>=3] -> the 22 984 + 9 577 rows recorded
+    in tests/golden/income_partitions.json."""
+    import json
+    import numpy as np
+    from conftest import GOLDEN
+    from anovos_b200.data_ingest import data_ingest as di
+    gold = json.load(open(os.path.join(GOLDEN, "income_partitions.json")))
+    big = tmp_path / "big.csv"
+    rng = np.random.default_rng(0)
+    lines = ["a,b,c"] + ["%d,%s,%.6f" % (i, "x" * int(rng.integers(0, 40)), rng.random()) for i in range(260_000)]
+    big.write_text("\n".join(lines) + "\n")
+    size = os.path.getsize(big)
+    assert size > 2 * di.OPEN_COST
+    parts = di.spark_file_partitions([str(big)], 16)
+    assert [(s, l) for p in parts for _, s, l in p] == [(o, min(di.OPEN_COST, size - o)) for o in range(0, size, di.OPEN_COST)]
+    rows = [sum(di.csv_rows_in_range(f, s, l, True) for f, s, l in p) for p in parts]
+    assert sum(rows) == 260_000 and len(rows) == -(-size // di.OPEN_COST)
+    starts = np.cumsum([0] + [len(x) + 1 for x in lines])[1:-1]            # data-line start offsets
+    brute = [int(((starts <= e) & (starts > (e - di.OPEN_COST if e > di.OPEN_COST else -1))).sum())
+             for e in range(di.OPEN_COST, size + di.OPEN_COST, di.OPEN_COST)]
+    assert rows == brute
+    assert len(di.spark_file_partitions([str(big)], 1)) == 1                  # one core: one split of the whole file
+    # small files are packed one per partition once their open cost is counted, largest first
+    small = []
+    for i, n in enumerate((3000, 5000, 4000)):
+        p = tmp_path / ("s%d.csv" % i)
+        p.write_text("a\n" + "1\n" * n)
+        small.append(str(p))
+    packed = di.spark_file_partitions(small, 8)
+    assert [os.path.basename(p[0][0]) for p in packed] == ["s1.csv", "s2.csv", "s0.csv"] and all(len(p) == 1 for p in packed)
+    fr = di.read_dataset(None, str(big), "csv", {"header": "True", "inferSchema": "True", "spark_cores": 16})
+    assert fr.spark_partitions and fr.chunk_rows == rows and fr.count() == 260_000 and fr.columns == ["a", "b", "c"]
+    assert gold["split_bytes"] == di.OPEN_COST and gold["file_bytes"] == 5891566 and gold["rows_per_partition"] == [22984, 9577]

@@ -293,6 +293,30 @@ def test_nb_percentiles_exact_with_spark_partitions(sg, income, nb_stats):
             assert (pd.isna(got[a][c]) and ora[a][c] is None) or got[a][c] == ora[a][c], (a, c)
 
 
+def test_read_dataset_as_spark_partitions(sg, income, tmp_path):
+    """read_dataset(..., spark_cores=N) scans a CSV the way Spark's local[N] would: product == the oracle's full sketch on
+    the same partitions (percentiles, medians, IQR), everything else == the unpartitioned result."""
+    import pyarrow.csv as pacsv
+    from anovos.data_ingest.data_ingest import read_dataset
+    num = [f.name for f in income.schema if not pa.types.is_string(f.type)]
+    path = str(tmp_path / "income.csv")
+    pacsv.write_csv(pa.concat_tables([income.select(num)] * 3), path)     # ~ 8 MB: 2-3 Hadoop splits
+    fr = read_dataset(None, path, "csv", {"header": "True", "inferSchema": "True", "spark_cores": 8})
+    assert fr.spark_partitions and fr.n_chunks >= 2 and fr.count() == 3 * income.num_rows
+    plain = read_dataset(None, path, "csv", {"header": "True", "inferSchema": "True"})
+    t = O.with_spark_partitions(pa.concat_tables([income.select(num)] * 3), fr.chunk_rows)
+    got, ora = frame_by_attr(sg.measures_of_percentiles(None, fr).toPandas()), frame_by_attr(O.measures_of_percentiles(t))
+    for a in ora:
+        for c in ["min", "max"] + list(S.SUMMARY_PCTS):
+            assert got[a][c] == ora[a][c], (a, c, got[a][c], ora[a][c])
+    d1, d2 = frame_by_attr(sg.measures_of_dispersion(None, fr).toPandas()), frame_by_attr(O.measures_of_dispersion(t))
+    for a in d2:
+        assert d1[a]["IQR"] == d2[a]["IQR"], a
+    for fn in ("measures_of_counts", "measures_of_shape", "measures_of_cardinality"):
+        a, b = getattr(sg, fn)(None, fr).toPandas(), getattr(sg, fn)(None, plain).toPandas()
+        assert a.drop(columns="attribute").round(4).equals(b.drop(columns="attribute").round(4)), fn
+
+
 def test_nb_drift(dd, income, income_source, nb_drift, tmp_path):
     df = dd.statistics(None, income, income_source, source_path=str(tmp_path)).toPandas()
     got, exp = frame_by_attr(df), table_by_attr(nb_drift[6])
