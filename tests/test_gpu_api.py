@@ -298,13 +298,12 @@ def test_read_dataset_as_spark_partitions(sg, income, tmp_path):
     the same partitions (percentiles, medians, IQR), everything else == the unpartitioned result."""
     import pyarrow.csv as pacsv
     from anovos.data_ingest.data_ingest import read_dataset
-    num = [f.name for f in income.schema if not pa.types.is_string(f.type)]
     path = str(tmp_path / "income.csv")
-    pacsv.write_csv(pa.concat_tables([income.select(num)] * 3), path)     # ~ 8 MB: 2-3 Hadoop splits
+    pacsv.write_csv(income, path)                                          # ~ 5.5 MB: two Hadoop splits at 4 MiB
     fr = read_dataset(None, path, "csv", {"header": "True", "inferSchema": "True", "spark_cores": 8})
-    assert fr.spark_partitions and fr.n_chunks >= 2 and fr.count() == 3 * income.num_rows
+    assert fr.spark_partitions and fr.n_chunks == 2 and fr.count() == income.num_rows and max(fr.chunk_rows) < 50000
     plain = read_dataset(None, path, "csv", {"header": "True", "inferSchema": "True"})
-    t = O.with_spark_partitions(pa.concat_tables([income.select(num)] * 3), fr.chunk_rows)
+    t = O.with_spark_partitions(income, fr.chunk_rows)
     got, ora = frame_by_attr(sg.measures_of_percentiles(None, fr).toPandas()), frame_by_attr(O.measures_of_percentiles(t))
     for a in ora:
         for c in ["min", "max"] + list(S.SUMMARY_PCTS):
