@@ -10,7 +10,9 @@ import pandas as pd
 
 class ResultFrame:
     def __init__(self, df: pd.DataFrame):
-        self._df = df.reset_index(drop=True)
+        idx = df.index
+        plain = isinstance(idx, pd.RangeIndex) and idx.start == 0 and idx.step == 1
+        self._df = df if plain else df.reset_index(drop=True)
 
     def toPandas(self) -> pd.DataFrame:
         return self._df.copy()

@@ -78,8 +78,13 @@ def spark_rank(n: int, p: float, eps) -> int:
     return int(pos[hit]) + 1
 
 
+@functools.lru_cache(maxsize=4096)
+def _spark_ranks(n: int, probs: tuple, eps):
+    return tuple(spark_rank(n, p, eps) for p in probs)
+
+
 def spark_ranks(n: int, probs, eps):
-    return [spark_rank(n, p, eps) for p in probs]
+    return list(_spark_ranks(int(n), tuple(probs), eps))
 
 
 # ---- several partitions: the sketches are merged in partition order (host arithmetic on a few thousand samples) ------
