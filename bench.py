@@ -10,8 +10,9 @@ percentiles / shape) of a synthetic float32 frame that is already resident in HB
 prints ONE JSON line.  `value` = rows x cols / s over all ranks (weak scaling: every rank
 owns `cols` columns - columns shard with no data-path collective, one NCCL all_gather of
 the per-column summaries per step).  `e2e` = the same step through the public API from
-pinned HOST buffers (H2D inside the timed region).  `roofline` describes the fused
-streaming scan kernel (K1) timed with CUDA events inside the timed region.
+pinned HOST buffers (H2D inside the timed region).  `roofline` describes the dominant C call of the
+step (the batched radix sort behind the exact mode), `roofline_kernels` the other calls (the fused
+streaming moments scan K1, HLL++), all timed with CUDA events inside the timed region.
 `--impl reference` times the CPU oracle restatement on the host cores (Spark is not
 available on the box).
 """
@@ -215,25 +216,42 @@ def _run_ours(args, out):
     ms_per_step = ms_max / args.steps
     value = rows * cols * world / (ms_per_step / 1e3)
 
-    # ---- roofline of the fused streaming scan kernel (K1), from the timed region -----------------
+    # ---- rooflines from the timed region: every C call of the step, the dominant one first ------------------
+    # algorithmic bytes per call: one read of values (+ bitmap) for the scan kernels; for the
+    # batched radix sort the minimal traffic of a 4-pass LSD sort of the non-null 32-bit keys: pack (read 4+b, write 4),
+    # per pass tile histogram (read 4) + stable scatter (read 4 + write 4), run summaries (read 4).
     n_nullable = sum(1 for c in src.columns if src.column(c).has_validity)
     alg_bytes = rows * cols * 4 + n_nullable * ((rows + 7) // 8)
-    k1 = kt.get("anv_moments", {"ms": 0.0, "calls": 0})
+    n_valid_total = int(sum(int(v) for v in engine.moments(src, src.columns)["n_valid"]))
+    alg = {"anv_moments": alg_bytes, "anv_hll_registers": alg_bytes, "anv_hist": alg_bytes, "anv_moments_hist": alg_bytes,
+           "anv_select_ranks": 3 * alg_bytes, "anv_mode_distinct": alg_bytes + n_valid_total * 4 * (1 + 4 * 3 + 1)}
+    names = {"anv_moments": "scan_kernel<MOM> (anv_moments: count/nonzero/min/max/mean/M2/M3/M4, FP64)",
+             "anv_mode_distinct": "batched 8-bit LSD radix sort + run summaries (anv_mode_distinct: pack, 4 x {sort_hist, sort_scan, "
+                                  "sort_scatter}, run_tile, run_merge) - exact mode / distinct / percentiles",
+             "anv_hll_registers": "hll_kernel (anv_hll_registers: XXH64 + HLL++ registers)"}
     peak, peak_src = peaks()
-    k1_ms = k1["ms"] / max(k1["calls"], 1)
-    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
-    traffic = None
-    try:  # dram__bytes_read+write per launch from the committed `ncu --set full` capture (same workload only)
+    traffic_tbl = {}
+    try:  # dram__bytes_read+write per call from the committed ncu capture (same workload only)
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if tj.get("rows") == rows and tj.get("cols") == cols:
-            traffic = tj["dram_bytes_per_launch"].get("anv_moments")
+            traffic_tbl = tj["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"kernel": "scan_kernel<MOM> (anv_moments: count/nonzero/min/max/mean/M2/M3/M4, FP64)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": traffic,
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k1_ms,
-                "share_of_step": k1["ms"] / ms if ms > 0 else None}
+
+    def roof(call):
+        v = kt[call]
+        ms_call = v["ms"] / max(v["calls"], 1)
+        ach = alg[call] / (ms_call * 1e-3) / 1e9 if (call in alg and ms_call > 0) else None
+        return {"kernel": names.get(call, call), "call": call, "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": traffic_tbl.get(call),
+                "algorithmic_bytes_per_launch": alg.get(call), "ms_per_launch": ms_call,
+                "launches_per_step": v["calls"] / args.steps, "share_of_step": v["ms"] / ms if ms > 0 else None}
+    by_share = sorted(kt, key=lambda c: -kt[c]["ms"])
+    roofline = roof(by_share[0]) if by_share else None
+    if roofline is not None and roofline["call"] == "anv_mode_distinct":
+        roofline["note"] = ("the sort is bound by integer issue (8 ballots + ranking per key and pass, about 90 instructions per key), "
+                            "not by HBM: see roofline_kernels for the HBM-bound scan kernels the step also runs")
+    roofline_kernels = [roof(c) for c in by_share[1:]]
     kernels = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
                    "share_of_step": v["ms"] / ms} for k, v in sorted(kt.items())}
 
@@ -264,8 +282,8 @@ def _run_ours(args, out):
                 "config": {"workload": args.workload + ": " + wl["desc"], "rows": rows, "cols_per_gpu": cols,
                            "l2": "inputs (%.1f GB per GPU) are larger than L2" % (rows * cols * 4 / 1e9),
                            "sharding": "columns per rank, one NCCL all_gather of per-column summaries per step"},
-                "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-                "kernels": kernels, "fused_stats_hist_pass": extra}
+                "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roofline,
+                "roofline_kernels": roofline_kernels, "cpu_baseline": cpu, "kernels": kernels, "fused_stats_hist_pass": extra}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -110,14 +110,6 @@ def full(rep, out, rows=None, cols=None):
         for r in recs:
             fh.write("| %s | " % r["kernel"] + " | ".join(
                 ("%.4g" % r[c]) if isinstance(r.get(c), float) else str(r.get(c, "")) for c in cols_md) + " |\n")
-    if rows and cols:
-        traffic = {}
-        for r in recs:
-            for pref, key in TRAFFIC_KEYS.items():
-                if r["kernel"].startswith(pref) and key not in traffic:
-                    traffic[key] = (r["dram_read_MB"] + r["dram_write_MB"]) * 1e6
-        json.dump({"workload": "c2", "rows": int(rows), "cols": int(cols), "source": out + ".md",
-                   "dram_bytes_per_launch": traffic}, open(os.path.join(os.path.dirname(out), "r1_traffic.json"), "w"), indent=1)
     print("wrote", out + ".md", len(recs), "kernels")
 
 
@@ -149,8 +141,50 @@ def launch(csv_path, out):
     print("wrote", out + ".md", len(agg), "kernels, total %.1f ms" % tot)
 
 
+CALL_OF = [(r"scan_kernel<1, \(int\)-1, 0>|finalize", "anv_moments"), (r"hll_kernel", "anv_hll_registers"),
+           (r"pack_kernel|sort_hist|sort_scan|sort_scatter|run_tile|run_merge", "anv_mode_distinct"),
+           (r"scan_kernel<0, (\(int\))?0, 0>", "anv_hist"), (r"scan_kernel<1, (\(int\))?0, 0>", "anv_moments_hist"),
+           (r"select_pass|select_scan", "anv_select_ranks")]
+CALL_MARK = {"anv_moments": r"finalize", "anv_hll_registers": r"hll_kernel", "anv_mode_distinct": r"run_merge",
+             "anv_hist": r"scan_kernel<0", "anv_moments_hist": r"finalize", "anv_select_ranks": None}
+
+
+def traffic(csv_path, out_json, rows, cols):
+    """`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list of a bench run -> DRAM bytes per
+    C call (all kernels the call launches), written to profiles/r1_traffic.json for bench.py's roofline.traffic."""
+    lines = [ln for ln in open(csv_path) if ln.startswith('"')]
+    rd = list(csv.reader(io.StringIO("".join(lines))))
+    hdr = rd[0]
+    kn, mn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    iid = hdr.index("ID")
+    bytes_of, marks, seen = {}, {}, set()
+    for r in rd[1:]:
+        if not r[mn].startswith("dram__bytes"):
+            continue
+        v = to_float(r[mv])
+        if v is None:
+            continue
+        v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[mu], 1.0)
+        for pat, call in CALL_OF:
+            if re.search(pat, r[kn]):
+                bytes_of[call] = bytes_of.get(call, 0.0) + v
+                mk = CALL_MARK.get(call)
+                if mk and re.search(mk, r[kn]) and (call, r[iid]) not in seen:
+                    seen.add((call, r[iid]))
+                    marks[call] = marks.get(call, 0) + 1
+                break
+    per_call = {c: b / max(marks.get(c, 1), 1) for c, b in bytes_of.items()}
+    json.dump({"workload": "c2", "rows": int(rows), "cols": int(cols), "source": os.path.basename(csv_path) +
+               " (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on `bench.py --steps 1 --warmup 1 --no-extras`; "
+               "bytes of every kernel a C call launches, per call)", "calls_captured": marks,
+               "dram_bytes_per_launch": per_call}, open(out_json, "w"), indent=1)
+    print("wrote", out_json, per_call, marks)
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "full":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
+    elif sys.argv[1] == "full":
         full(sys.argv[2], sys.argv[3], *(sys.argv[4:6]))
     else:
         launch(sys.argv[2], sys.argv[3])
