@@ -136,7 +136,7 @@ def hll(frame: ColumnFrame, names, rsd):
     return {n: c[n] for n in names}
 
 
-def prefetch(frame: ColumnFrame, names=None, want=("moments", "mode", "hll"), rsd=None, group: int = 10):
+def prefetch(frame: ColumnFrame, names=None, want=("moments", "mode", "hll"), rsd=None, group: int = 5):
     """Pipelined warm-up of the per-frame cache for a host-resident frame: every column's H2D
     copy is enqueued up front on a dedicated copy stream, and column group g is processed
     (moments -> sort-based mode/distinct/percentiles -> HLL++) while groups g+1.. are still in
