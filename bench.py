@@ -218,13 +218,13 @@ def _run_ours(args, out):
 
     # ---- rooflines from the timed region: every C call of the step, the dominant one first ------------------
     # algorithmic bytes per call: one read of values (+ bitmap) for the scan kernels; for the
-    # batched radix sort the minimal traffic of a 4-pass LSD sort of the non-null 32-bit keys: pack (read 4+b, write 4),
+    # batched radix sort the minimal traffic of a 4-pass LSD sort of the non-null, nonzero 32-bit keys: pack (read 4+b, write 4),
     # per pass tile histogram (read 4) + stable scatter (read 4 + write 4), run summaries (read 4).
     n_nullable = sum(1 for c in src.columns if src.column(c).has_validity)
     alg_bytes = rows * cols * 4 + n_nullable * ((rows + 7) // 8)
-    n_valid_total = int(sum(int(v) for v in engine.moments(src, src.columns)["n_valid"]))
+    n_keys = int(sum(int(v) for v in engine.moments(src, src.columns)["n_nonzero"]))   # exact zeros are counted, not sorted
     alg = {"anv_moments": alg_bytes, "anv_hll_registers": alg_bytes, "anv_hist": alg_bytes, "anv_moments_hist": alg_bytes,
-           "anv_select_ranks": 3 * alg_bytes, "anv_mode_distinct": alg_bytes + n_valid_total * 4 * (1 + 4 * 3 + 1)}
+           "anv_select_ranks": 3 * alg_bytes, "anv_mode_distinct": alg_bytes + n_keys * 4 * (1 + 4 * 3 + 1)}
     names = {"anv_moments": "scan_kernel<MOM> (anv_moments: count/nonzero/min/max/mean/M2/M3/M4, FP64)",
              "anv_mode_distinct": "batched 8-bit LSD radix sort + run summaries (anv_mode_distinct: pack, 4 x {sort_hist, sort_scan, "
                                   "sort_scatter}, run_tile, run_merge) - exact mode / distinct / percentiles",

@@ -209,9 +209,18 @@ def test_mode_distinct_exact(n):
     t = _mixed_table(n, seed=200 + n)
     t = t.append_column("i32_small", pa.array(rng.integers(0, 7, n).astype(np.int32), mask=rng.random(n) < 0.2))
     t = t.append_column("f32_signed", pa.array(np.round(rng.normal(0, 3, n)).astype(np.float32)))
+    # exact zeros are counted by the pack kernel and spliced back in: all-zero, zeros + nulls, -0.0, zero-inflated with
+    # negatives on the left and a tie between the zero run and another value
+    t = t.append_column("all_zero", pa.array(np.zeros(n, np.float32)))
+    t = t.append_column("zero_or_null", pa.array(np.zeros(n, np.int64), mask=rng.random(n) < 0.5))
+    zi = np.where(rng.random(n) < 0.6, 0.0, np.round(rng.normal(0, 50, n), 1))
+    zi[rng.random(n) < 0.1] = -0.0
+    t = t.append_column("f64_zero_inflated", pa.array(zi, mask=rng.random(n) < 0.05))
+    tie = np.concatenate([np.zeros(n // 3), np.full(n // 3, -2.5), np.arange(n - 2 * (n // 3)) + 1.0])
+    t = t.append_column("f32_zero_tie", pa.array(rng.permutation(tie).astype(np.float32)))
     fr = ColumnFrame.from_arrow(t)
     names = t.column_names
-    probs = [0.01, 0.25, 0.5, 0.75, 0.99, 1.0]
+    probs = [0.01, 0.25, 0.4, 0.5, 0.6, 0.75, 0.99, 1.0]
     rk = []
     for c in names:
         vals, valid = S.column_values(t, c)
