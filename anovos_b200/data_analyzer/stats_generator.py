@@ -16,7 +16,7 @@ import pandas as pd
 from .. import profile
 from ..frame import as_frame
 from ..result import ResultFrame
-from ..shared.utils import attributeType_segregation, jvm_double_str, spark_round
+from ..shared.utils import attributeType_segregation, jvm_double_str, spark_round, spark_round_array
 
 _R = spark_round
 
@@ -55,6 +55,16 @@ def _disp(col, v):
     if col.sdtype == "float":
         return float(str(np.float32(v)))
     return float(v)
+
+
+def _disp_array(col, values):
+    """_disp over a list of floats / None -> float64 array (None -> NaN)."""
+    a = np.array([np.nan if v is None else v for v in values], dtype=np.float64)
+    if col.sdtype == "float":
+        ok = np.isfinite(a)
+        if ok.any():
+            a[ok] = a[ok].astype(np.float32).astype("U32").astype(np.float64)   # Float.toString round trip
+    return a
 
 
 def global_summary(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
@@ -301,15 +311,15 @@ def measures_of_percentiles(spark, idf, list_of_cols="all", drop_cols=[], print_
         return _empty(names)
     m = profile.moments(fr, cols)
     q = profile.quantiles(fr, cols, [p for _, p in _PCT])
-    rows = []
-    for c in cols:
-        col, rec = fr.column(c), m[c]
-        if int(rec["n_valid"]) == 0:
-            rows.append([c] + [None] * 11)
-            continue
-        rows.append([c, _R(_disp(col, float(rec["min"])))] + [_R(_disp(col, v)) for v in q[c]]
-                    + [_R(_disp(col, float(rec["max"])))])
-    return _show(ResultFrame(pd.DataFrame(rows, columns=names)), len(cols), print_impact)
+    vals = np.full((len(cols), 11), np.nan)
+    for i, c in enumerate(cols):
+        rec = m[c]
+        if int(rec["n_valid"]):
+            vals[i] = _disp_array(fr.column(c), [float(rec["min"])] + list(q[c]) + [float(rec["max"])])
+    vals = spark_round_array(vals)
+    odf = pd.DataFrame(vals, columns=names[1:])
+    odf.insert(0, "attribute", cols)
+    return _show(ResultFrame(odf), len(cols), print_impact)
 
 
 def measures_of_shape(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):

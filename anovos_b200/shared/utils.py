@@ -47,6 +47,23 @@ def spark_round(x, scale=4):
     return float(Decimal(repr(x)).quantize(q, rounding=ROUND_HALF_UP))
 
 
+def spark_round_array(x, scale=4):
+    """Vectorised spark_round over a float64 array (NaN = null stays NaN): the fast path is exact away from decimal
+    ties (rint(x * 10^scale) / 10^scale is then the correctly rounded double of the decimal value); elements near a tie
+    go through the decimal slow path one by one."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float64)
+    if scale != 4:
+        return np.array([np.nan if v != v else spark_round(v, scale) for v in x.ravel().tolist()]).reshape(x.shape)
+    with np.errstate(invalid="ignore", over="ignore"):
+        t = x * 10000.0
+        safe = (np.abs(t) < 1e11) & (np.abs((t - np.floor(t)) - 0.5) > 1e-6 + np.abs(t) * 2e-15)
+        out = np.where(safe, np.rint(t) / 10000.0, x)
+    for i in np.flatnonzero(~safe.ravel() & np.isfinite(x.ravel())):
+        out.ravel()[i] = spark_round(float(x.ravel()[i]), 4)
+    return out
+
+
 def jvm_double_str(x: float) -> str:
     """java.lang.Double.toString of x: decimal notation for 1e-3 <= |x| < 1e7, otherwise
     d.dddE[-]n (what `mode` looks like after the reference casts it to string,
