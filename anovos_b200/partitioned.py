@@ -18,9 +18,11 @@ so the data itself never moves between GPUs.  Equal-range binning is the 2-step 
 survey names: pass 1 merges min/max, the cutoffs are computed on the host (identically on every
 rank), pass 2 histograms every partition against them.  The reference functions
 (stats_generator, attribute_binning, drift statistics) accept a PartitionedFrame wherever they
-accept a frame; the exact mode / exact distinct count of NUMERIC columns needs a global group-by
-and is the one thing a row partition cannot merge - use `repartition_to_columns` (all-to-all
-over NVLink, every rank ends up with whole columns) or the approximate distinct count instead.
+accept a frame.  The exact mode / exact distinct count of NUMERIC columns needs a global group-by,
+the one thing row partitions cannot merge: there the partitions are turned into whole columns
+first - local chunks are concatenated on the device, row slabs are exchanged with
+`repartition_to_columns` (all-to-all over NVLink, every rank ends up with whole columns of its
+block), each rank sorts its block and the per-column results are all-gathered.
 """
 from __future__ import annotations
 
@@ -404,18 +406,43 @@ class PartitionedFrame:
 
     def sort_mode_distinct(self, names, ranks=None):
         """Exact mode / distinct count of numeric columns needs whole columns.  Local chunks are concatenated on the
-        device when they fit (a chunked host table, a Spark-partitioned table); row slabs on several ranks must be
-        exchanged first (repartition_to_columns)."""
+        device; row slabs on several ranks are first exchanged (repartition_to_columns: every rank receives whole
+        columns of its block over NVLink), each rank sorts its block and the small per-column results are
+        all-gathered, so every rank returns the full answer."""
         from . import engine
         torch = _lib.require_cuda()
         names = list(names)
-        need = sum(self.n_rows_local * (8 if self.column(n).anv_dtype in (_lib.ANV_F64, _lib.ANV_I64) else 4) for n in names)
-        if self.group is not None or 3 * need > torch.cuda.mem_get_info()[0]:
+        need = sum(self.n_rows * (8 if self.column(n).anv_dtype in (_lib.ANV_F64, _lib.ANV_I64) else 4) for n in names)
+        if 3 * need // (self.group.world if self.group is not None else 1) > torch.cuda.mem_get_info()[0]:
             raise NotImplementedError(
-                "exact mode / exact distinct count of numeric columns needs a global group-by, which row partitions "
-                "cannot merge: call partitioned.repartition_to_columns(frame) first (all-to-all, each rank then owns "
-                "whole columns), or use the approximate distinct count (HLL++)")
-        return engine.sort_mode_distinct(self.materialize(names), names, ranks)
+                "exact mode / exact distinct count of numeric columns needs whole columns in HBM, which this frame "
+                "does not fit: use the approximate distinct count (HLL++) or fewer columns per call")
+        local = self.materialize(names)
+        if self.group is None:
+            return engine.sort_mode_distinct(local, names, ranks)
+        if self.group.group is not None:
+            raise NotImplementedError("row-slab exchange is implemented on the default process group only")
+        from . import parallel
+        block = repartition_to_columns(local, True, names)
+        del local
+        mine = block.columns
+        n_ranks = 0 if ranks is None else np.asarray(ranks).reshape(len(names), -1).shape[1]
+        rk = None if ranks is None else np.asarray(ranks, dtype=np.int64).reshape(len(names), -1)[[names.index(n) for n in mine]]
+        mat = np.zeros((len(mine), 3 + n_ranks), np.float64)
+        if mine:
+            res = engine.sort_mode_distinct(block, mine, rk)
+            modes, rvals = res if ranks is not None else (res, None)
+            for i, (mv, mr, nd) in enumerate(modes):
+                mat[i, :3] = (np.nan if mv is None else mv, -1 if mr is None else mr, nd)
+            if n_ranks:
+                mat[:, 3:] = rvals
+        full = np.concatenate(parallel.gather_summaries(mat, device="cuda" if self.group.device == "cuda" else None))
+        order = [n for r in range(self.group.world) for n in parallel.shard_columns(names, r, self.group.world)]
+        by = {n: full[i] for i, n in enumerate(order)}
+        out = [((float(by[n][0]), int(by[n][1]), int(by[n][2])) if by[n][1] >= 0 else (None, None, 0)) for n in names]
+        if ranks is None:
+            return out
+        return out, np.array([by[n][3:] for n in names], dtype=np.float64).reshape(len(names), n_ranks)
 
 
 # ---- row slabs -> column blocks (the one real exchange step) ---------------------------------------

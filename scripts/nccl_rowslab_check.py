@@ -51,6 +51,10 @@ b = dd.statistics(None, tparts, parts, source_path="/tmp/anv_nccl_p%d" % rank, *
 for m in ("PSI", "HD", "JSD", "KS"):
     assert np.allclose(a[m], b[m], rtol=1e-9, atol=0), m
 assert list(a["flagged"]) == list(b["flagged"])
+# exact mode on the row slabs directly (exchange + sort + all_gather under the hood)
+cw_all = sg.measures_of_centralTendency(None, whole).toPandas()
+cp_all = sg.measures_of_centralTendency(None, parts).toPandas()
+assert cw_all.equals(cp_all), (cw_all, cp_all)
 # the exchange over NVLink: slabs -> whole columns of this rank's block, then exact mode / distinct
 mine = repartition_to_columns(slab, True)
 names = parallel.shard_columns(slab.columns, rank, world)

@@ -193,11 +193,10 @@ def _rank_worker(rank, world, port, ret):
     out = {"count": parts.count(), "mom": engine.moments(parts, slab.columns).tolist()}
     for fn in ("measures_of_counts", "measures_of_percentiles", "measures_of_cardinality", "measures_of_shape"):
         out[fn] = getattr(sg, fn)(None, parts).toPandas().to_dict("list")
-    try:   # row slabs on several ranks cannot merge a numeric mode: the caller must exchange first
-        sg.mode_computation(None, parts, num[:1])
-        out["mode_error"] = False
-    except NotImplementedError:
-        out["mode_error"] = True
+    # exact mode / distinct on row slabs: the slabs are exchanged into column blocks under the hood and the per-column
+    # results all-gathered, so every rank holds the whole table
+    out["central_slabs"] = sg.measures_of_centralTendency(None, parts).toPandas().to_dict("list")
+    out["unique_slabs"] = sg.uniqueCount_computation(None, parts).toPandas().to_dict("list")
     out["drift"] = dd.statistics(None, tparts, parts, method_type="all", use_sampling=False,
                                  source_path="/tmp/anv_part_test_%d_%d" % (port, rank)).toPandas().to_dict("list")
     # (b) the exchange: row slabs -> whole columns of this rank's block, then the full column path (incl. exact mode)
@@ -223,7 +222,9 @@ def test_two_ranks_row_slabs_match_single_frame(tmp_path):
     for k in ("count", "mom", "measures_of_counts", "measures_of_percentiles", "measures_of_cardinality",
               "measures_of_shape", "drift"):
         assert repr(a[k]) == repr(b[k]), k                      # every rank takes the same decisions
-    assert a["count"] == ROWS and a["mode_error"] and b["mode_error"]
+    assert a["count"] == ROWS
+    for k in ("central_slabs", "unique_slabs"):
+        assert repr(a[k]) == repr(b[k]), k
     mw = engine.moments(whole, whole.columns)
     mp_ = np.array([tuple(r) for r in a["mom"]], dtype=engine._MOM_DT)
     for f in ("n_valid", "n_nonzero", "min", "max"):
@@ -240,6 +241,8 @@ def test_two_ranks_row_slabs_match_single_frame(tmp_path):
     assert list(dw["flagged"]) == a["drift"]["flagged"]
     # after the exchange each rank owns whole columns: the concatenation is the single-frame result
     cw = sg.measures_of_centralTendency(None, whole).toPandas()
+    _same_table(cw, pd.DataFrame(a["central_slabs"]))
+    _same_table(sg.uniqueCount_computation(None, whole).toPandas(), pd.DataFrame(a["unique_slabs"]))
     cp = pd.concat([pd.DataFrame(a["central"]), pd.DataFrame(b["central"])], ignore_index=True)
     _same_table(cw, cp)
     uw = sg.uniqueCount_computation(None, whole).toPandas()
