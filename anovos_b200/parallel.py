@@ -15,15 +15,25 @@ def shard_columns(names, rank: int, world: int):
     return names[rank * per:(rank + 1) * per]
 
 
+_NON_NUMERIC = {"attribute", "mode", "metric", "value"}
+
+
 def frames_to_matrix(frames):
     """Result frames (pandas) -> float64 matrix [n_attributes, n_numeric_fields] + the field names.
     Non-numeric fields (attribute, mode) stay local to the rank; they are re-attached by name."""
+    import pandas as pd
     cols, names = [], []
     for df in frames:
-        num = df.drop(columns=[c for c in df.columns if c in ("attribute", "mode", "metric", "value")])
-        cols.append(num.to_numpy(dtype=np.float64, na_value=np.nan))
-        names += list(num.columns)
-    return np.ascontiguousarray(np.concatenate(cols, axis=1)), names
+        for c in df.columns:
+            if c in _NON_NUMERIC:
+                continue
+            a = df[c]._values
+            if a.dtype != np.float64:
+                a = (pd.to_numeric(df[c], errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
+                     if a.dtype == object else np.asarray(a, dtype=np.float64))
+            cols.append(a)
+            names.append(c)
+    return np.ascontiguousarray(np.stack(cols, axis=1)), names
 
 
 class PendingGather:
