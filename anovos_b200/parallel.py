@@ -28,9 +28,10 @@ def frames_to_matrix(frames):
             if c in _NON_NUMERIC:
                 continue
             a = df[c]._values
-            if a.dtype != np.float64:
-                a = (pd.to_numeric(df[c], errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
-                     if a.dtype == object else np.asarray(a, dtype=np.float64))
+            if isinstance(a, np.ndarray) and a.dtype != object:
+                a = a.astype(np.float64, copy=False)
+            else:                       # object columns (None for "not applicable"), pandas extension arrays
+                a = pd.to_numeric(df[c], errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
             cols.append(a)
             names.append(c)
     return np.ascontiguousarray(np.stack(cols, axis=1)), names
