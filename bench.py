@@ -240,12 +240,14 @@ def _run_ours(args, out):
 
     def roof(call):
         v = kt[call]
-        ms_call = v["ms"] / max(v["calls"], 1)
-        ach = alg[call] / (ms_call * 1e-3) / 1e9 if (call in alg and ms_call > 0) else None
+        per_step = v["calls"] / args.steps                 # a step may batch the columns over several launches (c3 sort)
+        ms_step = v["ms"] / args.steps                     # device time of this call per step
+        ach = alg[call] / (ms_step * 1e-3) / 1e9 if (call in alg and ms_step > 0) else None
         return {"kernel": names.get(call, call), "call": call, "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": traffic_tbl.get(call),
-                "algorithmic_bytes_per_launch": alg.get(call), "ms_per_launch": ms_call,
-                "launches_per_step": v["calls"] / args.steps, "share_of_step": v["ms"] / ms if ms > 0 else None}
+                "algorithmic_bytes_per_launch": alg[call] / per_step if call in alg else None,
+                "ms_per_launch": ms_step / per_step, "launches_per_step": per_step,
+                "share_of_step": v["ms"] / ms if ms > 0 else None}
     by_share = sorted(kt, key=lambda c: -kt[c]["ms"])
     roofline = roof(by_share[0]) if by_share else None
     if roofline is not None and roofline["call"] == "anv_mode_distinct":
