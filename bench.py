@@ -567,14 +567,17 @@ def e2e_numbers(args, rows, cols, host, torch, framemod, engine):
     one()
     torch.cuda.synchronize()
     h0, d0 = framemod.h2d_bytes, engine.d2h_bytes
-    t0 = time.perf_counter()
+    times = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         one()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / steps
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / steps
     return {"value": rows * cols / dt, "unit": "rows*cols/s", "ms_per_step": dt * 1e3,
+            "ms_each_step": [round(t * 1e3, 2) for t in times],
             "h2d_bytes_per_step": (framemod.h2d_bytes - h0) // steps, "d2h_bytes_per_step": (engine.d2h_bytes - d0) // steps,
-            "steps": steps, "note": "pinned host columns -> pipelined H2D (profile.prefetch) -> 6 measures_of_* -> pandas, wall clock incl. host post-processing"}
+            "steps": steps, "note": "pinned host columns -> pipelined H2D (profile.prefetch) -> 6 measures_of_* -> pandas, wall clock incl. host post-processing; mean over the steps (each listed: PCIe time varies with what else the host is doing)"}
 
 
 # ---------------------------------------------------------------------------------------------
