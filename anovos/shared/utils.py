@@ -1,1 +1,2 @@
-from anovos_b200.shared.utils import attributeType_segregation, get_dtype, ends_with  # noqa: F401
+from anovos_b200.shared.utils import (  # noqa: F401
+    attributeType_segregation, get_dtype, ends_with, flatten_dataframe, transpose_dataframe)

@@ -29,6 +29,42 @@ def ends_with(string, end_str="/"):
     return string if string.endswith(end_str) else string + end_str
 
 
+def _small_frame(idf):
+    """Result-sized frames only (the reference reshapes `summary()` outputs with these helpers)."""
+    import pandas as pd
+    if hasattr(idf, "toPandas"):
+        return idf.toPandas()
+    if isinstance(idf, pd.DataFrame):
+        return idf
+    raise TypeError("flatten_dataframe / transpose_dataframe reshape small result frames (ResultFrame or pandas)")
+
+
+def flatten_dataframe(idf, fixed_cols):
+    """reference shared/utils.py:6-26: every column not in fixed_cols is melted into (key, value) rows - Spark's
+    `explode(create_map(...))`: for each input row, one output row per melted column, in column order."""
+    from ..result import ResultFrame
+    df = _small_frame(idf)
+    fixed_cols = list(fixed_cols)
+    valid = [c for c in df.columns if c not in fixed_cols]
+    out = df.melt(id_vars=fixed_cols, value_vars=valid, var_name="key", value_name="value")
+    order = {c: i for i, c in enumerate(valid)}
+    out = out.assign(_r=list(range(len(df))) * len(valid), _k=out["key"].map(order)).sort_values(["_r", "_k"])
+    return ResultFrame(out.drop(columns=["_r", "_k"]).reset_index(drop=True))
+
+
+def transpose_dataframe(idf, fixed_col):
+    """reference shared/utils.py:29-45: `groupBy("key").pivot(fixed_col).agg(first("value"))` - one row per melted
+    column, one output column per distinct value of fixed_col (sorted, like Spark's pivot)."""
+    from ..result import ResultFrame
+    flat = flatten_dataframe(idf, [fixed_col]).toPandas()
+    keys = list(dict.fromkeys(flat["key"].tolist()))
+    cols = sorted(flat[fixed_col].dropna().unique().tolist())
+    first = flat.groupby(["key", fixed_col], sort=False)["value"].first()
+    rows = [[k] + [first.get((k, c)) for c in cols] for k in keys]
+    import pandas as pd
+    return ResultFrame(pd.DataFrame(rows, columns=["key"] + [str(c) for c in cols]))
+
+
 def spark_round(x, scale=4):
     """F.round(double, scale): HALF_UP on the shortest decimal repr of the double."""
     if x is None:

@@ -78,3 +78,17 @@ def test_spark_scan_partitions(tmp_path):
     fr = di.read_dataset(None, str(big), "csv", {"header": "True", "inferSchema": "True", "spark_cores": 16})
     assert fr.spark_partitions and fr.chunk_rows == rows and fr.count() == 260_000 and fr.columns == ["a", "b", "c"]
     assert gold["split_bytes"] == di.OPEN_COST and gold["file_bytes"] == 5891566 and gold["rows_per_partition"] == [22984, 9577]
+
+
+def test_flatten_and_transpose_dataframe():
+    """shared/utils.py:6-45 on a summary()-shaped frame: explode(create_map) row order, pivot columns sorted."""
+    import pandas as pd
+    from anovos.shared.utils import flatten_dataframe, transpose_dataframe
+    df = pd.DataFrame({"summary": ["count", "mean", "max"], "age": [4, 42.75, 55], "income": [3, 7333.3, 9000]})
+    flat = flatten_dataframe(df, ["summary"]).toPandas()
+    assert flat.columns.tolist() == ["summary", "key", "value"]
+    assert flat[["summary", "key"]].values.tolist() == [["count", "age"], ["count", "income"], ["mean", "age"], ["mean", "income"],
+                                                          ["max", "age"], ["max", "income"]]
+    tr = transpose_dataframe(df, "summary").toPandas()
+    assert tr.columns.tolist() == ["key", "count", "max", "mean"]
+    assert tr.values.tolist() == [["age", 4.0, 55.0, 42.75], ["income", 3.0, 9000.0, 7333.3]]
