@@ -8,13 +8,14 @@
 // code histograms already hold the group counts).
 //
 // Pipeline (all columns of the call advance together, grid.y = column):
-//   pack     values -> keys, nulls dropped (warp-aggregated unordered compaction: the order
-//            before a sort is irrelevant), n_valid counted on the device;
-//   8-bit LSD passes: tile histogram -> per-column exclusive scan -> stable scatter
-//            (per-warp match_any ranking); a pass whose digit is constant is skipped
-//            (device-side decision, no host sync) - float data rarely needs all bytes;
-//   runs     per-tile run summary of the sorted keys (head count, open prefix / suffix run,
-//            longest closed run) merged sequentially per column.
+//   pack     values -> keys, nulls dropped, exact zeros counted instead of sorted (block compaction: the order
+//            before a sort is irrelevant), key count per column kept on the device;
+//   8-bit LSD passes: tile histogram -> per-column exclusive scan -> stable scatter (8-ballot peer ranking,
+//            shared-memory reorder); a pass in which one digit holds every key is skipped (device-side
+//            decision taken from the scanned table, no host sync);
+//   runs     per-thread run summaries of 16 consecutive sorted keys (head count, open prefix / suffix run,
+//            longest closed run), combined with an associative operator per warp, per tile and per column;
+//            the merge kernel splices the zero run back and reads the requested order statistics.
 // Counting is integer everywhere => deterministic.  Ties for the mode resolve to the
 // smallest value (the reference's choice is arbitrary, stats_generator.py:358).
 #include "common.cuh"
@@ -81,7 +82,6 @@ template <typename K> struct SortParams {
   K* buf[2];
   ColState* state;
   uint32_t* tile_hist;          // [n_cols][256][n_tiles]  (digit-major)
-  unsigned long long* digit_total;  // [n_cols][256]
   TileSummary<K>* summ;         // [n_cols][n_tiles]
   int pass;
 };
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
 }
 
 template <typename K> struct Layout {
-  size_t state, buf0, buf1, tile_hist, digit_total, summ, total;
+  size_t state, buf0, buf1, tile_hist, summ, total;
   Layout(int n_cols, int64_t n_rows) {
     const int64_t stride = (n_rows + 63) & ~(int64_t)63;
     const int64_t n_tiles = (n_rows + SORT_TILE - 1) / SORT_TILE;
@@ -611,7 +611,6 @@ template <typename K> struct Layout {
     buf0 = take((size_t)n_cols * stride * sizeof(K));
     buf1 = take((size_t)n_cols * stride * sizeof(K));
     tile_hist = take((size_t)n_cols * 256 * (n_tiles > 0 ? n_tiles : 1) * 4);
-    digit_total = take((size_t)n_cols * 256 * 8);
     summ = take((size_t)n_cols * (n_tiles > 0 ? n_tiles : 1) * sizeof(TileSummary<K>));
     total = o + 256;
   }
@@ -633,7 +632,6 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   P.buf[1] = reinterpret_cast<K*>(w + L.buf1);
   P.state = reinterpret_cast<ColState*>(w + L.state);
   P.tile_hist = reinterpret_cast<uint32_t*>(w + L.tile_hist);
-  P.digit_total = reinterpret_cast<unsigned long long*>(w + L.digit_total);
   P.summ = reinterpret_cast<TileSummary<K>*>(w + L.summ);
   ANV_CUDA(cudaMemsetAsync(P.state, 0, (size_t)n_cols * sizeof(ColState), st));
   if (n_rows > 0) {

@@ -31,6 +31,9 @@ WORKLOADS = {
     "c2": dict(rows=10_000_000, cols=50, desc="synthetic 10M rows x 50 float32 cols: full stats_generator"),
     "c3": dict(rows=100_000_000, cols=200, desc="synthetic 100M rows x 200 float32 cols: full stats_generator"),
     "tiny": dict(rows=200_000, cols=8, desc="smoke-size synthetic frame"),
+    # BASELINE.json configs[0], the reference's own CPU-runnable plumbing check ("always report C1")
+    "c1": dict(rows=32_561, cols=17, c1=True, desc="income dataset (data/test_dataset, 32 561 x 17: 7 int + 1 double + 9 string): "
+                                                   "measures_of_centralTendency"),
     # streamed workloads (BASELINE.json configs[3], [4]): the frames do not fit HBM, row chunks are (re)generated on the
     # device pass by pass; step = drift statistics(all methods) + counts/shape of both frames from the same passes
     "c4": dict(rows=100_000_000, cols=200, chunk=12_500_000, cat_every=4, stream=True,
@@ -159,6 +162,8 @@ def _run_ours(args, out):
     rows, cols = args.rows or wl["rows"], args.cols or wl["cols"]
     if wl.get("stream"):
         return _run_stream(args, out, wl, rows, cols, world, rank, local)
+    if wl.get("c1"):
+        return _run_c1(args, out, wl, world, rank, local)
 
     def barrier():
         torch.cuda.synchronize()
@@ -291,6 +296,104 @@ def _run_ours(args, out):
         dist.destroy_process_group()
     if line is not None:
         out.emit(json.dumps(line))
+
+
+def _same_cells(a, b):
+    """Cell-wise equality of two result tables (null == null)."""
+    import pandas as pd
+    if list(a.columns) != list(b.columns) or len(a) != len(b):
+        return False
+    for c in a.columns:
+        for x, y in zip(a[c].tolist(), b[c].tolist()):
+            if not ((pd.isna(x) and pd.isna(y)) or x == y):
+                return False
+    return True
+
+
+def income_table():
+    """data/test_dataset of the reference = the two parquet parts committed under tests/golden/."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    g = os.path.join(ROOT, "tests", "golden")
+    return pa.concat_tables([pq.read_table(os.path.join(g, "income_part0.parquet")), pq.read_table(os.path.join(g, "income_part1.parquet"))])
+
+
+def _run_c1(args, out, wl, world, rank, local):
+    """configs[0]: measures_of_centralTendency on the income dataset.  A plumbing check, not a throughput claim: 32 561
+    rows fit in L2, the step is launch- and host-bound.  `value` from the device-resident frame, `e2e` from the pyarrow
+    table (conversion + H2D inside), `cpu_baseline` = the oracle in this process (1 core)."""
+    import torch
+    import anovos.data_analyzer.stats_generator as sg
+    from anovos_b200 import engine, frame as framemod
+    from oracle import api as O
+    if rank != 0:
+        return
+    t = income_table()
+    rows, cols = t.num_rows, t.num_columns
+    fr = framemod.ColumnFrame.from_arrow(t)
+    for c in fr.columns:
+        if fr.column(c).kind != "other":
+            fr.column(c).device()
+
+    def step():
+        fr._cache = {k: v for k, v in fr._cache.items() if isinstance(k, tuple) and k and k[0] == "desc"}
+        return sg.measures_of_centralTendency(None, fr).toPandas()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    engine.timer = engine.KernelTimer()
+    l0 = engine.launch_count
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    kt = engine.timer.totals()
+    engine.timer = None
+    launches = engine.launch_count - l0
+    h0, d0 = framemod.h2d_bytes, engine.d2h_bytes
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sg.measures_of_centralTendency(None, t).toPandas()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    e2e = {"value": rows * cols / dt, "unit": "rows*cols/s", "ms_per_step": dt * 1e3,
+           "h2d_bytes_per_step": (framemod.h2d_bytes - h0) // args.steps, "d2h_bytes_per_step": (engine.d2h_bytes - d0) // args.steps,
+           "note": "pyarrow table -> ColumnFrame (dictionary encoding on the host) -> H2D -> measures_of_centralTendency -> pandas"}
+    t0 = time.perf_counter()
+    exp = O.measures_of_centralTendency(t)
+    tc = time.perf_counter() - t0
+    by = sorted(kt, key=lambda c: -kt[c]["ms"])
+    peak, peak_src = peaks()
+    top = by[0] if by else None
+    from anovos_b200 import _lib as L_
+    nbytes = rows * sum(4 if fr.column(c).anv_dtype in (L_.ANV_F32, L_.ANV_I32) else 8 for c in fr.columns if fr.column(c).kind != "other")
+    roofline = None
+    if top:
+        ms_step = kt[top]["ms"] / args.steps
+        ach = nbytes / (ms_step * 1e-3) / 1e9
+        roofline = {"kernel": top, "call": top, "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms_step /
+                    max(kt[top]["calls"] / args.steps, 1), "share_of_step": kt[top]["ms"] / ms,
+                    "note": "1.8 MB of input: latency-bound by construction, the fraction is not meaningful at this size"}
+    line = {"metric": "rows x cols / s, measures_of_centralTendency on the income dataset (reference plumbing check)",
+            "value": rows * cols / (ms / args.steps / 1e3), "unit": "rows*cols/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "tests/golden/income_part{0,1}.parquet (= data/test_dataset of the reference)",
+            "config": {"workload": args.workload + ": " + wl["desc"], "rows": rows, "cols_per_gpu": cols,
+                       "l2": "input (1.8 MB) is SMALLER than L2: plumbing check only"},
+            "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roofline,
+            "cpu_baseline": {"value": rows * cols / tc, "unit": "rows*cols/s", "cores": 1, "kind": "port",
+                             "sample": "the whole dataset, oracle measures_of_centralTendency in this process, %.3f s" % tc},
+            "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps} for k, v in sorted(kt.items())},
+            "matches_oracle": _same_cells(res, exp)}
+    out.emit(json.dumps(line))
 
 
 STREAM_METRIC = "rows x cols / s, streamed fused stats + drift_statistics (source + target, + HBM GB/s of the fused pass)"
@@ -618,6 +721,25 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
+    if wl.get("c1"):
+        from oracle import api as O
+        t = income_table()
+        times = []
+        for i in range(max(args.warmup, 1) + args.steps):
+            t0 = time.perf_counter()
+            O.measures_of_centralTendency(t)
+            if i >= max(args.warmup, 1):
+                times.append(time.perf_counter() - t0)
+        dt = sum(times) / len(times)
+        v = t.num_rows * t.num_columns / dt
+        print(json.dumps({"impl": "reference", "metric": "rows x cols / s, measures_of_centralTendency on the income dataset "
+                          "(reference plumbing check)", "value": v, "unit": "rows*cols/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "tests/golden/income_part{0,1}.parquet",
+                          "config": {"workload": args.workload + ": " + wl["desc"], "rows": t.num_rows, "cols_per_gpu": t.num_columns},
+                          "cpu_baseline": {"value": v, "unit": "rows*cols/s", "cores": 1, "kind": "port", "sample": "the whole dataset"},
+                          "e2e": {"value": v, "unit": "rows*cols/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     cols = args.cols or wl["cols"]
     rows = min(args.rows or wl["rows"], CPU_SAMPLE_ROWS)
     from anovos_b200 import synth
