@@ -140,7 +140,7 @@ def nonzeroCount_computation(spark, idf, list_of_cols="all", drop_cols=[], print
         return _empty(["attribute", "nonzero_count", "nonzero_pct"])
     N = fr.count()
     m = profile.moments(fr, cols)
-    rows = [[c, int(m[c]["n_nonzero"]), _R(int(m[c]["n_nonzero"]) / N)] for c in cols]
+    rows = [[c, int(m[c]["n_nonzero"]), _R(int(m[c]["n_nonzero"]) / N) if N else None] for c in cols]   # x / 0: null
     return _show(ResultFrame(pd.DataFrame(rows, columns=["attribute", "nonzero_count", "nonzero_pct"])),
                  len(cols), print_impact)
 
@@ -155,11 +155,11 @@ def measures_of_counts(spark, idf, list_of_cols="all", drop_cols=[], print_impac
     rows = []
     for c in cols:
         fill = nv[c]
-        fill_pct = _R(fill / N)
-        row = [c, fill, fill_pct, N - fill, _R(1 - fill_pct)]
+        fill_pct = _R(fill / N) if N else None
+        row = [c, fill, fill_pct, N - fill, None if fill_pct is None else _R(1 - fill_pct)]
         if fr.column(c).kind == "num":
             nz = int(m[c]["n_nonzero"])
-            row += [nz, _R(nz / N)]
+            row += [nz, _R(nz / N) if N else None]
         else:
             row += [None, None]
         rows.append(row)

@@ -235,7 +235,7 @@ def nonzeroCount_computation(table, list_of_cols="all", drop_cols=[]):
     rows = []
     for c, p in _profiles(table, cols).items():
         nz = p.nonzero()
-        rows.append([c, nz, R(nz / N)])
+        rows.append([c, nz, R(nz / N) if N else None])          # x / 0 is null in Spark SQL
     return pd.DataFrame(rows, columns=["attribute", "nonzero_count", "nonzero_pct"])
 
 
@@ -247,11 +247,11 @@ def measures_of_counts(table, list_of_cols="all", drop_cols=[]):
     N = table.num_rows
     rows = []
     for c, p in _profiles(table, cols).items():
-        fill_pct = R(p.n / N)
-        row = [c, p.n, fill_pct, N - p.n, R(1 - fill_pct)]       # :313-319
+        fill_pct = R(p.n / N) if N else None
+        row = [c, p.n, fill_pct, N - p.n, None if fill_pct is None else R(1 - fill_pct)]       # :313-319
         if c in num_sel:
             nz = p.nonzero()
-            row += [nz, R(nz / N)]
+            row += [nz, R(nz / N) if N else None]
         else:
             row += [None, None]
         rows.append(row)

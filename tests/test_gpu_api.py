@@ -410,6 +410,33 @@ def test_drift_vs_oracle(dd, tmp_path, n, bin_method, bins):
         assert np.allclose(again[m].values.astype(float), got[m].values.astype(float), rtol=1e-9, atol=1e-12), m
 
 
+def test_empty_and_all_null_frames(sg, dd, tr, tmp_path):
+    """Edge frames (parity unpinned: no reference test has them): zero rows, all-null columns, a single row.
+    The product must not crash and must agree with the oracle cell for cell (nulls included)."""
+    frames = {
+        "empty": pa.table({"a": pa.array([], pa.float32()), "b": pa.array([], pa.int64()), "s": pa.array([], pa.string())}),
+        "all_null": pa.table({"a": pa.array([None] * 5, pa.float64()), "b": pa.array([1, 2, None, 4, 5], pa.int32()),
+                              "s": pa.array([None] * 5, pa.string())}),
+        "one_row": pa.table({"a": pa.array([2.5], pa.float32()), "b": pa.array([7], pa.int64()), "s": pa.array(["x"])}),
+    }
+    for name, t in frames.items():
+        for fn in ("global_summary", "measures_of_counts", "measures_of_centralTendency", "measures_of_cardinality",
+                   "measures_of_dispersion", "measures_of_percentiles", "measures_of_shape", "missingCount_computation",
+                   "nonzeroCount_computation", "mode_computation"):
+            got, exp = getattr(sg, fn)(None, t).toPandas(), getattr(O, fn)(t)
+            assert list(got.columns) == list(exp.columns) and len(got) == len(exp), (name, fn)
+            for c in got.columns:
+                for x, y in zip(got[c].tolist(), exp[c].tolist()):
+                    assert (pd.isna(x) and (y is None or pd.isna(y))) or x == y or str(x) == str(y), (name, fn, c, x, y)
+    # binning and drift on the all-null frame: column a is dropped with a warning, b is binned
+    with pytest.warns(UserWarning):
+        out = tr.attribute_binning(None, frames["all_null"], bin_size=3)
+    assert out.columns == ["a", "b", "s"]
+    r = dd.statistics(None, frames["all_null"], frames["all_null"], method_type="all", use_sampling=False,
+                      source_path=str(tmp_path)).toPandas()
+    assert r["attribute"].tolist() == ["a", "b", "s"] and r["flagged"].tolist() == [0, 0, 0]
+
+
 def test_prefetch_pipeline_matches_direct(sg):
     """profile.prefetch (async grouped upload + passes) must give the same frames as the lazy path."""
     import torch
