@@ -67,6 +67,45 @@ def _disp_array(col, values):
     return a
 
 
+_F32_EPS = 2.0 ** -23
+
+
+def _f32_trip(a):
+    """Float.toString round trip of float32-representable doubles (vectorised; slow: ~1 us per value)."""
+    return a.astype(np.float32).astype("U32").astype(np.float64)
+
+
+def _near_tie(x, unc):
+    """Could changing x by at most `unc` change round(x, 4)?"""
+    with np.errstate(invalid="ignore", over="ignore"):
+        t = x * 10000.0
+        return ~(np.abs((t - np.floor(t)) - 0.5) > unc * 10000.0 + 1e-6) & np.isfinite(x)
+
+
+def _disp_matrix(fr, cols, vals):
+    """_disp over a [n_cols, k] float64 matrix (NaN = null) whose entries are about to be ROUNDED to 4 decimals: the rows
+    of FloatType columns take the Float.toString round trip, which moves a value by less than half a float32 ulp - so
+    only the entries that sit within that distance of a rounding tie are actually converted."""
+    rows = [i for i, c in enumerate(cols) if fr.column(c).sdtype == "float"]
+    if rows:
+        sub = vals[rows]
+        need = _near_tie(sub, np.abs(sub) * _F32_EPS)
+        if need.any():
+            sub[need] = _f32_trip(sub[need])
+            vals[rows] = sub
+    return vals
+
+
+def _disp_diff(fr, cols, hi, lo):
+    """round-ready `_disp(hi) - _disp(lo)` per column (IQR, range) with the same shortcut."""
+    d = hi - lo
+    rows = np.array([fr.column(c).sdtype == "float" for c in cols], dtype=bool)
+    need = rows & _near_tie(d, (np.abs(hi) + np.abs(lo)) * _F32_EPS)
+    if need.any():
+        d[need] = _f32_trip(hi[need]) - _f32_trip(lo[need])
+    return d
+
+
 def global_summary(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
     """reference :33-113 - every value is a string."""
     fr = as_frame(idf)
@@ -279,20 +318,21 @@ def measures_of_dispersion(spark, idf, list_of_cols="all", drop_cols=[], print_i
         return _empty(["attribute", "stddev", "variance", "cov", "IQR", "range"])
     m = profile.moments(fr, cols)
     q = profile.quantiles(fr, cols, [0.25, 0.75])
-    rows = []
-    for c in cols:
-        col, rec = fr.column(c), m[c]
-        if int(rec["n_valid"]) == 0:
-            rows.append([c, None, None, None, None, None])
-            continue
-        sd = _R(_stddev(rec))
-        mean = float(rec["mean"])
-        var = None if sd is None else _R(sd * sd)
-        cov = None if (sd is None or mean == 0) else _R(sd / mean)   # x / 0 is null in Spark SQL
-        iqr = _R(_disp(col, q[c][1]) - _disp(col, q[c][0]))
-        rng = _R(_disp(col, float(rec["max"])) - _disp(col, float(rec["min"])))
-        rows.append([c, sd, var, cov, iqr, rng])
-    odf = pd.DataFrame(rows, columns=["attribute", "stddev", "variance", "cov", "IQR", "range"])
+    k = len(cols)
+    nv = np.array([int(m[c]["n_valid"]) for c in cols])
+    m2 = np.array([float(m[c]["m2"]) for c in cols])
+    mean = np.array([float(m[c]["mean"]) for c in cols])
+    raw = np.full((k, 4), np.nan)                     # q25, q75, min, max (display values)
+    for i, c in enumerate(cols):
+        if nv[i]:
+            raw[i] = (q[c][0], q[c][1], float(m[c]["min"]), float(m[c]["max"]))
+    with np.errstate(all="ignore"):
+        sd = spark_round_array(np.where(nv > 1, np.sqrt(m2 / np.maximum(nv - 1, 1)), np.nan))   # n <= 1: null (Spark >= 3.1)
+        var = spark_round_array(sd * sd)
+        cov = spark_round_array(np.where(mean == 0, np.nan, sd / mean))                           # x / 0 is null in Spark SQL
+        iqr = spark_round_array(_disp_diff(fr, cols, raw[:, 1].copy(), raw[:, 0].copy()))
+        rng = spark_round_array(_disp_diff(fr, cols, raw[:, 3].copy(), raw[:, 2].copy()))
+    odf = pd.DataFrame({"attribute": cols, "stddev": sd, "variance": var, "cov": cov, "IQR": iqr, "range": rng})
     return _show(ResultFrame(odf), len(cols), print_impact)
 
 
@@ -315,8 +355,9 @@ def measures_of_percentiles(spark, idf, list_of_cols="all", drop_cols=[], print_
     for i, c in enumerate(cols):
         rec = m[c]
         if int(rec["n_valid"]):
-            vals[i] = _disp_array(fr.column(c), [float(rec["min"])] + list(q[c]) + [float(rec["max"])])
-    vals = spark_round_array(vals)
+            vals[i, 0], vals[i, 10] = rec["min"], rec["max"]
+            vals[i, 1:10] = [np.nan if v is None else v for v in q[c]]
+    vals = spark_round_array(_disp_matrix(fr, cols, vals))
     odf = pd.DataFrame(vals, columns=names[1:])
     odf.insert(0, "attribute", cols)
     return _show(ResultFrame(odf), len(cols), print_impact)

@@ -12,6 +12,7 @@ import numpy as np
 
 from . import _lib
 from .frame import ColumnFrame
+from .shared import gk as _gk
 
 _NP_OF_ANV = {_lib.ANV_F32: np.float32, _lib.ANV_F64: np.float64, _lib.ANV_I32: np.int32, _lib.ANV_I64: np.int64}
 
@@ -317,8 +318,7 @@ def quantile_ranks(n_valid: int, probs, eps=None):
     eps None: the exact rule max(1, ceil(p * n)) with p * n in float64.  eps = the relativeError of
     the Spark call being replaced (1e-4 for summary(), 0.01 for approxQuantile): the Greenwald-Khanna sketch
     position for one partition of < 50 000 values, the exact rule beyond (shared/gk.py)."""
-    from .shared import gk
-    return gk.spark_ranks(int(n_valid), probs, eps)
+    return _gk.spark_ranks(int(n_valid), probs, eps)
 
 
 def select_ranks(frame: ColumnFrame, names, ranks):

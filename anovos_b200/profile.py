@@ -57,16 +57,22 @@ def quantiles(frame: ColumnFrame, names, probs, eps=SUMMARY_EPS):
             return {n: [gc[(n, p)] for p in probs] for n in names}
     c = _cache(frame, "quantiles")
     mom = moments(frame, names)
-    want, extra = {}, {}
+    rc = _cache(frame, "quantile_ranks")
+    pk = (tuple(probs), eps)
+    want = {}
     for n in names:
-        nv = int(mom[n]["n_valid"])
-        want[n] = engine.quantile_ranks(nv, probs, eps)
-        # a select pass costs the same for 1 or 16 ranks: always resolve the nine summary()
-        # percentiles too, so median / IQR / percentiles share ONE radix select per column
-        extra[n] = engine.quantile_ranks(nv, SUMMARY_PROBS, SUMMARY_EPS)
+        r = rc.get((n, pk))
+        if r is None:
+            r = rc[(n, pk)] = engine.quantile_ranks(int(mom[n]["n_valid"]), probs, eps)
+        want[n] = r
     todo = [n for n in names if any(r and (n, r) not in c for r in want[n])]
     if todo:
-        sets = {n: sorted(set(r for r in want[n] + extra[n] if r and (n, r) not in c)) for n in todo}
+        # a select pass costs the same for 1 or 16 ranks: always resolve the nine summary() percentiles too, so
+        # median / IQR / percentiles share ONE radix select per column
+        sets = {}
+        for n in todo:
+            extra = engine.quantile_ranks(int(mom[n]["n_valid"]), SUMMARY_PROBS, SUMMARY_EPS)
+            sets[n] = sorted(set(r for r in want[n] + extra if r and (n, r) not in c))
         width = max(len(v) for v in sets.values())
         rk = np.zeros((len(todo), max(width, 1)), np.int64)
         for i, n in enumerate(todo):
