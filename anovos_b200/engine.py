@@ -437,6 +437,25 @@ def hll_estimate_from_registers(regs: np.ndarray, p: int):
     return int(math.floor(e + 0.5)), True
 
 
+def hll_estimates_from_register_rows(R: np.ndarray, p: int):
+    """hll_estimate_from_registers for every row of R [n_cols, 2**p] at once -> list of (estimate, in_bias_band)."""
+    m = 1 << p
+    Ri = R.astype(np.int64)
+    z = np.ldexp(1.0, -Ri).sum(axis=1)
+    v = (Ri == 0).sum(axis=1)
+    alpha = {4: 0.673, 5: 0.697, 6: 0.709}.get(p, 0.7213 / (1.0 + 1.079 / m))
+    e = alpha * m * m / z
+    out = []
+    for ei, vi in zip(e.tolist(), v.tolist()):
+        if vi > 0:
+            h = m * math.log(m / vi)
+            if h <= _HLL_T[p]:
+                out.append((int(math.floor(h + 0.5)), False))
+                continue
+        out.append((int(math.floor(ei + 0.5)), not (ei >= 5.0 * m)))
+    return out
+
+
 def hll_registers(frame: ColumnFrame, names, p: int):
     """-> uint32 [n_cols, 2**p] HLL++ registers of NUMERIC columns (max-mergeable across row partitions)."""
     if getattr(frame, "is_partitioned", False):
@@ -465,8 +484,8 @@ def hll_estimates(frame: ColumnFrame, names, p: int):
     cat = [n for n in names if frame.column(n).kind == "cat"]
     if num:
         R = hll_registers(frame, num, p)
-        for i, n in enumerate(num):
-            out[n] = hll_estimate_from_registers(R[i], p)
+        for n, r in zip(num, hll_estimates_from_register_rows(R, p)):
+            out[n] = r
     if cat:
         # per-row work (the code histogram) runs on the device; only the dictionary entries that
         # actually occur are hashed on the host, once each
