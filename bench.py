@@ -667,7 +667,8 @@ def e2e_numbers(args, rows, cols, host, torch, framemod, engine):
         del fr
         return r
 
-    one()
+    for _ in range(max(args.warmup, 3)):   # the copy-stream memory pool needs a few rounds to reach its steady size
+        one()
     torch.cuda.synchronize()
     h0, d0 = framemod.h2d_bytes, engine.d2h_bytes
     times = []
