@@ -1,0 +1,67 @@
+"""Host-side arithmetic of the product that has a scalar definition and a vectorised fast path: the fast path must be
+bit-identical.  CPU only (no kernel is launched)."""
+import numpy as np
+import pandas as pd
+
+from anovos_b200 import engine, parallel
+from anovos_b200.data_analyzer import stats_generator as sg
+from anovos_b200.shared.utils import jvm_double_str, spark_round, spark_round_array
+from oracle import spark_semantics as S
+
+
+def test_spark_round_array_equals_scalar_half_up():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(0, 100, 20000), rng.normal(0, 1e6, 5000), np.round(rng.normal(0, 10, 5000), 4) + 0.00005,
+                        [0.12345, 1.00005, 2.5e-5, -0.00005, 1e12, -1e15, 0.0, np.nan, np.inf]])
+    got = spark_round_array(x)
+    exp = np.array([np.nan if v != v else spark_round(v) for v in x.tolist()])
+    assert np.array_equal(got, exp, equal_nan=True)
+    assert spark_round(0.12345) == S.round_half_up(0.12345) == 0.1235      # HALF_UP on the shortest repr, not half-even
+    assert np.array_equal(spark_round_array(np.array([[0.00005, np.nan]])), np.array([[0.0001, np.nan]]), equal_nan=True)
+
+
+def test_float32_display_shortcut_is_exact():
+    """Float.toString round trip of FloatType values is skipped when it cannot change round(x, 4): same result as
+    always converting, for single values and for differences (IQR, range)."""
+    rng = np.random.default_rng(1)
+    for scale in (1e-3, 1.0, 30.0, 1e3, 1e5):
+        x = rng.normal(0, scale, 50000).astype(np.float32).astype(np.float64)
+        full = spark_round_array(sg._f32_trip(x))
+        need = sg._near_tie(x, np.abs(x) * sg._F32_EPS)
+        y = x.copy()
+        y[need] = sg._f32_trip(y[need])
+        assert np.array_equal(full, spark_round_array(y)), scale
+        a = rng.normal(0, scale, 50000).astype(np.float32).astype(np.float64)
+        b = (a + np.abs(rng.normal(0, scale, 50000))).astype(np.float32).astype(np.float64)
+        d = b - a
+        nd = sg._near_tie(d, (np.abs(a) + np.abs(b)) * sg._F32_EPS)
+        d[nd] = sg._f32_trip(b[nd]) - sg._f32_trip(a[nd])
+        assert np.array_equal(spark_round_array(sg._f32_trip(b) - sg._f32_trip(a)), spark_round_array(d)), scale
+    assert sg._f32_trip(np.array([np.float64(np.float32(0.1))]))[0] == 0.1
+
+
+def test_hll_estimates_rows_equal_scalar():
+    rng = np.random.default_rng(2)
+    for p in (4, 9, 12, 14):
+        R = rng.integers(0, 25, (30, 1 << p)).astype(np.uint32)
+        R[:5] = 0
+        R[5:10] = (rng.random((5, 1 << p)) < 0.02) * 3
+        R[10:15] = (rng.random((5, 1 << p)) < 0.6) * rng.integers(1, 4, (5, 1 << p))
+        assert engine.hll_estimates_from_register_rows(R, p) == [engine.hll_estimate_from_registers(R[i], p) for i in range(30)]
+        assert engine.hll_estimate_from_registers(R[0], p) == (0, False)
+
+
+def test_jvm_double_strings():
+    for x, s in ((1.0, "1.0"), (5.093362141, "5.093362141"), (1e7, "1.0E7"), (12345678.9, "1.23456789E7"), (0.001, "0.001"),
+                 (0.0001, "1.0E-4"), (-0.0, "-0.0"), (float("nan"), "NaN"), (float("inf"), "Infinity"), (100.0, "100.0")):
+        assert jvm_double_str(x) == s, (x, jvm_double_str(x))
+        assert S.java_double_to_string(x) == s
+
+
+def test_frames_to_matrix_mixed_dtypes():
+    f1 = pd.DataFrame({"attribute": ["a", "b"], "mean": [1.5, None], "mode": ["x", None], "mode_rows": [3, None]})
+    f2 = pd.DataFrame({"attribute": ["a", "b"], "count": np.array([4, 5], dtype=np.int64),
+                       "nullable": pd.array([1, None], dtype="Int64")})
+    m, names = parallel.frames_to_matrix([f1, f2])
+    assert names == ["mean", "mode_rows", "count", "nullable"]
+    assert np.array_equal(m, np.array([[1.5, 3, 4, 1], [np.nan, np.nan, 5, np.nan]]), equal_nan=True)
