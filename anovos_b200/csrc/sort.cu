@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(ANV_BLOCK) pack_kernel(const SortParams<K> P) 
   }
 }
 
-// Lanes of `act` holding the same 8-bit digit: per bit one predicate test, one ballot and one predicated
-// AND / AND-NOT (4 SASS instructions per bit; the C++ form compiles to 6).
-#define ANV_PEER_BIT(B)                                                                              \
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, bal;\n\tand.b32 t, %1, " #B ";\n\tsetp.ne.u32 p, t, 0;\n\t"     \
-               "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t@p and.b32 %0, %0, bal;\n\t"                 \
-               "@!p lop3.b32 %0, %0, bal, 0, 0x30;\n\t}"                                                 \
+// Lanes of `act` holding the same 8-bit digit.  Per bit: test, ballot of "my bit is set", and ONE three-input logic op
+// m &= ballot ^ (my bit ? 0 : ~0)  - keep the lanes whose bit equals mine (4 SASS instructions per bit + the select).
+#define ANV_PEER_BIT(B)                                                                                       \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, bal, s;\n\tand.b32 t, %1, " #B ";\n\tsetp.ne.u32 p, t, 0;\n\t"     \
+               "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\tselp.b32 s, 0, -1, p;\n\t"                               \
+               "lop3.b32 %0, %0, bal, s, 0x60;\n\t}"                                                          \
                : "+r"(m) : "r"(d))
 __device__ __forceinline__ uint32_t peers8(uint32_t d, uint32_t act) {
   uint32_t m = act;
