@@ -328,22 +328,25 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortParams<K> P) 
 // masks are computed up front (independent), then the warp-private digit counters are advanced
 // round by round.  The tile is then REORDERED IN SHARED MEMORY into digit order, so the global
 // writes are coalesced runs (full 32-byte sectors) instead of 4-byte scatters.
-template <typename K>
-__global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const SortParams<K> P) {
-  const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const ColState& S = P.state[c];
-  if (S.skip[P.pass]) return;
-  const int64_t n = (int64_t)S.n_valid;
-  const int64_t t0 = (int64_t)tile * SORT_TILE;
-  if (t0 >= n) return;
-  const int nt = (int)min((int64_t)SORT_TILE, n - t0);
+template <typename K> struct ScatShared {   // declared ONCE in the kernel (statics in the templated body would be replicated)
+  uint16_t wcnt[SCAT_WARPS][256];             // <= 4096 keys per tile: 16 bits are enough
+  uint32_t gbase[256];
+  uint32_t wtot[8];
+  K sk[SORT_TILE + 1];                        // + the spare slot of the branch-free placement
+};
+
+template <typename K, bool FULL>
+__device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColState& S, const int c, const int tile, const int64_t t0,
+                                             const int nt_in, ScatShared<K>& SH) {
+  auto& wcnt = SH.wcnt;
+  auto& gbase = SH.gbase;
+  auto& wtot = SH.wtot;
+  auto& sk = SH.sk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = FULL ? SORT_TILE : nt_in;   // a full tile needs no bounds logic (all but the last tile of a column)
   const int src = S.src[P.pass];
   const K* __restrict__ in = (src ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride + t0;
   K* __restrict__ out = (src ? P.buf[0] : P.buf[1]) + (size_t)c * P.stride;
-  __shared__ uint16_t wcnt[SCAT_WARPS][256];  // <= 4096 keys per tile: 16 bits are enough
-  __shared__ uint32_t gbase[256];
-  __shared__ uint32_t wtot[8];
-  __shared__ K sk[SORT_TILE];
   for (int i = tid; i < SCAT_WARPS * 256 / 2; i += SCAT_THREADS) reinterpret_cast<uint32_t*>(&wcnt[0][0])[i] = 0;
   if (tid < 256) gbase[tid] = P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile];
   constexpr int WR = SORT_TILE / SCAT_WARPS / 32;  // 8 rounds per warp
@@ -353,13 +356,13 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
     const int i = w0 + r * 32 + lane;
-    key[r] = (i < nt) ? in[i] : (K)0;
+    key[r] = (FULL || i < nt) ? in[i] : (K)0;
   }
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
-    const bool ok = (w0 + r * 32 + lane) < nt;
-    const uint32_t act = __ballot_sync(ANV_FULL, ok);
+    const bool ok = FULL || (w0 + r * 32 + lane) < nt;
+    const uint32_t act = FULL ? ANV_FULL : __ballot_sync(ANV_FULL, ok);
     const uint32_t d = digit_of(key[r], P.pass);
     const uint32_t m = peers8(d, act);
     peers[r] = ok ? m : 0u;
@@ -372,9 +375,10 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
     const uint32_t d = digit_of(key[r], P.pass);
     uint32_t before = 0;
     if (m) before = wcnt[warp][d];
-    pos[r] = before + __popc(m & lt);
+    const uint32_t lower = m & lt;               // peers in lower lanes: none <=> this lane leads its group
+    pos[r] = before + __popc(lower);
     __syncwarp();
-    if (m && lane == __ffs(m) - 1) wcnt[warp][d] = (uint16_t)(before + __popc(m));
+    if (m && lower == 0) wcnt[warp][d] = (uint16_t)(before + __popc(m));
     __syncwarp();
   }
   __syncthreads();
@@ -408,17 +412,39 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < WR; ++r) {
-    if (peers[r]) {
-      const uint32_t d = digit_of(key[r], P.pass);
-      sk[wcnt[warp][d] + pos[r]] = key[r];
-    }
+  for (int r = 0; r < WR; ++r) {   // branch-free: lanes past the end of a partial tile write to the spare slot
+    const uint32_t d = digit_of(key[r], P.pass);
+    const uint32_t at = wcnt[warp][d] + pos[r];
+    sk[(FULL || peers[r]) ? at : (uint32_t)SORT_TILE] = key[r];
   }
   __syncthreads();
-  for (int p = tid; p < nt; p += SCAT_THREADS) {
-    const K k = sk[p];
-    out[(size_t)(gbase[digit_of(k, P.pass)] + (uint32_t)p)] = k;
+  if (FULL) {
+#pragma unroll
+    for (int j = 0; j < SORT_TILE / SCAT_THREADS; ++j) {
+      const int p = tid + j * SCAT_THREADS;
+      const K k = sk[p];
+      out[(size_t)(gbase[digit_of(k, P.pass)] + (uint32_t)p)] = k;
+    }
+  } else {
+    for (int p = tid; p < nt; p += SCAT_THREADS) {
+      const K k = sk[p];
+      out[(size_t)(gbase[digit_of(k, P.pass)] + (uint32_t)p)] = k;
+    }
   }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const SortParams<K> P) {
+  const int c = blockIdx.y, tile = blockIdx.x;
+  const ColState& S = P.state[c];
+  if (S.skip[P.pass]) return;
+  const int64_t n = (int64_t)S.n_valid;
+  const int64_t t0 = (int64_t)tile * SORT_TILE;
+  if (t0 >= n) return;
+  const int nt = (int)min((int64_t)SORT_TILE, n - t0);
+  __shared__ ScatShared<K> SH;
+  if (nt == SORT_TILE) scatter_tile<K, true>(P, S, c, tile, t0, nt, SH);
+  else scatter_tile<K, false>(P, S, c, tile, t0, nt, SH);
 }
 
 // Associative combine of two ADJACENT run summaries (left, right) of sorted keys.
