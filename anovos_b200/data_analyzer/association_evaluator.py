@@ -79,6 +79,14 @@ def _masked(fr: ColumnFrame, names, words) -> ColumnFrame:
 
 def _prepare(idf, list_of_cols, drop_cols, label_col, event_label, encoding_configs):
     fr = as_frame(idf)
+    if getattr(fr, "is_partitioned", False):
+        # chunked / Spark-partitioned table: the cutoffs come from the partitioned frame (so approxQuantile follows Spark's
+        # per-partition sketches), the label-class histograms from the concatenated columns
+        if fr.group is not None:
+            raise NotImplementedError("IV / IG on row slabs of several ranks: repartition_to_columns first")
+        part = fr
+        fr = part.materialize()
+        fr._cut_source = part
     if label_col not in fr.columns:
         raise TypeError("Invalid input for Label Column")
     if isinstance(list_of_cols, str) and list_of_cols == "all":
@@ -112,7 +120,8 @@ def _contingency(fr, cols, num, cat, ev_w, nev_w, binned, encoding_configs):
     views = {"all": fr, "ev": _masked(fr, cols, ev_w), "nev": _masked(fr, cols, nev_w)}
     hists = {}
     if num:
-        kept, cuts, lohi = compute_cutoffs(fr, num, encoding_configs["bin_method"], encoding_configs["bin_size"])
+        kept, cuts, lohi = compute_cutoffs(getattr(fr, "_cut_source", fr), num, encoding_configs["bin_method"],
+                                           encoding_configs["bin_size"])
         for k, f in views.items():
             model = engine.BinModel(f, kept, cuts, lohi)
             h = engine.histogram(f, model)
@@ -186,14 +195,16 @@ def IG_calculation(spark, idf, list_of_cols="all", drop_cols=[], label_col="labe
     rows = []
     for c in cols:
         a, e, ne = tab[c]
-        s = 0.0
+        s, any_term = 0.0, False
         for g in range(len(a)):
             if a[g] == 0:
                 continue
             p = float(e[g]) / float(a[g])
             if 0 < p < 1:
                 s += -(float(a[g]) / n) * (p * math.log2(p) + (1 - p) * math.log2(1 - p))
-        rows.append([c, total_entropy - s])
+                any_term = True
+        # Spark's sum over all-NULL segment entropies is NULL (id-like column: every segment pure) -> null ig
+        rows.append([c, total_entropy - s if any_term else None])
     odf = ResultFrame(pd.DataFrame(rows, columns=["attribute", "ig"]))
     if print_impact:
         odf.show(len(cols))

@@ -163,6 +163,12 @@ class ColumnProfile:
             return float(S.quantile_sorted(self.sorted64, p))
         return float(self.sorted64[S.gk_query_position(sm, self.n, eps, p)])
 
+    def equal_frequency_cutoffs(self, bin_size):
+        """transformers.py:210-215: approxQuantile(cols, [j * (1 / bin_size)], 0.01) - through the same sketch logic as
+        every other percentile (one partition / Spark partitions of the table / exact beyond the head buffer)."""
+        w = 1 / bin_size
+        return [self.quantile(j * w, S.APPROX_QUANTILE_EPS) for j in range(1, bin_size)]
+
     def nonzero(self):
         if self.n == 0:
             return 0
@@ -428,7 +434,7 @@ def binning_cutoffs(table, cols, method_type="equal_range", bin_size=10):
                 cuts.append([float("nan")] * (bin_size - 1))  # approxQuantile on empty: unpinned
                 continue
             kept.append(c)
-            cuts.append(S.equal_frequency_cutoffs(p.sorted64, bin_size))
+            cuts.append(p.equal_frequency_cutoffs(bin_size))
         else:
             if p.n == 0:
                 dropped.append(c)                       # :226-228
@@ -774,11 +780,22 @@ def _encoded_groups(table, col, encoding_configs):
         bs, bm = encoding_configs["bin_size"], encoding_configs["bin_method"]
         if p.n == 0:
             return np.array([None] * p.N, dtype=object)
-        cut = S.equal_frequency_cutoffs(p.sorted64, bs) if bm == "equal_frequency" else \
-            S.equal_range_cutoffs(*p.minmax(), bs)
+        cut = p.equal_frequency_cutoffs(bs) if bm == "equal_frequency" else S.equal_range_cutoffs(*p.minmax(), bs)
         ids = S.assign_bins(p.values.astype(np.float64), p.valid, cut, bs)
         return np.array([int(k) if ok else None for k, ok in zip(ids, p.valid)], dtype=object)
     return np.array([(v if ok else None) for v, ok in zip(p.values.tolist(), p.valid)], dtype=object)
+
+
+def _group_counts_by_class(keys, nev, ev):
+    """groupBy(attribute): per group (null = its own group) -> (non-event rows, event rows, all rows) as floats."""
+    is_null = np.array([k is None for k in keys.tolist()])
+    labels = np.array(["\0null" if k is None else ("s" + k if isinstance(k, str) else "n%r" % (k,)) for k in keys.tolist()], dtype=object)
+    _, inv = np.unique(labels.astype(str), return_inverse=True)
+    g = int(inv.max()) + 1 if inv.size else 0
+    l0 = np.bincount(inv, weights=nev.astype(np.float64), minlength=g)
+    l1 = np.bincount(inv, weights=ev.astype(np.float64), minlength=g)
+    tc = np.bincount(inv, minlength=g).astype(np.float64)
+    return list(zip(l0.tolist(), l1.tolist(), tc.tolist()))
 
 
 def _iv_ig_cols(table, list_of_cols, drop_cols, label_col, event_label):
@@ -807,9 +824,7 @@ def IV_calculation(table, list_of_cols="all", drop_cols=[], label_col="label", e
         keys = _encoded_groups(table, c, encoding_configs)
         t0, t1 = float(nev.sum()), float(ev.sum())
         iv = 0.0
-        for g in set(keys.tolist()):
-            m = np.array([k == g for k in keys.tolist()]) if g is not None else np.array([k is None for k in keys.tolist()])
-            l0, l1 = float((m & nev).sum()), float((m & ev).sum())
+        for l0, l1, _ in _group_counts_by_class(keys, nev, ev):
             ne, e = l0 / t0, l1 / t1
             woe = math.log(ne / e) if (ne != 0 and e != 0) else math.log(((l0 + 0.5) / t0) / ((l1 + 0.5) / t1))
             iv += woe * (ne - e)
@@ -828,13 +843,15 @@ def IG_calculation(table, list_of_cols="all", drop_cols=[], label_col="label", e
     for c in cols:
         keys = _encoded_groups(table, c, encoding_configs)
         s = 0.0
-        for g in set(keys.tolist()):
-            m = np.array([k == g for k in keys.tolist()]) if g is not None else np.array([k is None for k in keys.tolist()])
-            tc, ec = float(m.sum()), float((m & ev).sum())     # count(label) after the when/otherwise recode: every row
+        any_term = False
+        for _, ec, tc in _group_counts_by_class(keys, nev, ev):    # count(label) after the when/otherwise recode: every row
             p = ec / tc
             if 0 < p < 1:
                 s += -(tc / n) * (p * math.log2(p) + (1 - p) * math.log2(1 - p))
-        rows.append([c, total_entropy - s])
+                any_term = True
+        # F.sum over segments whose entropy is NULL everywhere is NULL (an id-like column: every segment pure), pinned
+        # by the reference notebook (ifa: NaN)
+        rows.append([c, total_entropy - s if any_term else None])
     return pd.DataFrame(rows, columns=["attribute", "ig"])
 
 

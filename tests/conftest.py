@@ -50,5 +50,23 @@ def nb_stats():
 
 
 @pytest.fixture(scope="session")
+def nb_quality():
+    return {t["code_cell"]: t for t in _tables("notebook_quality.json")}
+
+
+@pytest.fixture(scope="session")
+def nb_assoc():
+    return {t["code_cell"]: t for t in _tables("notebook_association.json")}
+
+
+@pytest.fixture(scope="session")
+def income_spark(income):
+    """The income table tagged with the scan partitions Spark used when the reference notebooks ran."""
+    import json
+    from oracle import api as O
+    return O.with_spark_partitions(income, json.load(open(os.path.join(GOLDEN, "income_partitions.json")))["rows_per_partition"])
+
+
+@pytest.fixture(scope="session")
 def nb_drift():
     return {t["code_cell"]: t for t in _tables("notebook_drift.json")}

@@ -16,6 +16,8 @@ reference stores in its notebooks, plus the input datasets they were computed on
                           spark.sql.files.openCostInBytes = 4 MiB (any local[*] with >= 3 cores) -> rows per partition
   notebook_stats.json     stored outputs of examples/notebooks/data_analyzer__stats_generator.ipynb
   notebook_drift.json     stored outputs of examples/notebooks/drift_stability.ipynb
+  notebook_quality.json   stored outputs of examples/notebooks/data_analyzer__quality_checker.ipynb
+  notebook_association.json  stored outputs of examples/notebooks/data_analyzer__association_evaluator.ipynb
 """
 import html.parser
 import json
@@ -135,6 +137,10 @@ def main():
               open(OUT + "/notebook_stats.json", "w"), indent=0)
     json.dump(notebook_tables(REF + "/examples/notebooks/drift_stability.ipynb"),
               open(OUT + "/notebook_drift.json", "w"), indent=0)
+    json.dump(notebook_tables(REF + "/examples/notebooks/data_analyzer__quality_checker.ipynb"),
+              open(OUT + "/notebook_quality.json", "w"), indent=0)
+    json.dump(notebook_tables(REF + "/examples/notebooks/data_analyzer__association_evaluator.ipynb"),
+              open(OUT + "/notebook_association.json", "w"), indent=0)
     json.dump(csv_partition_rows(REF + "/examples/data/income_dataset/csv/part-00000-8beb3930-8a44-4b7b-906b-a6deca466d9f-c000.csv"),
               open(OUT + "/income_partitions.json", "w"))
     print(inc.schema, inc.num_rows, src.num_rows)

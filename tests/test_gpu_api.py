@@ -604,3 +604,46 @@ def test_iv_ig(income_part0):
     ts = income_part0
     a = ae.IV_calculation(None, ts, list_of_cols=["sex", "age"], label_col="income", event_label=">50K").toPandas()
     assert abs(a.set_index("attribute").loc["sex", "iv"] - 0.3111) < 5e-5
+
+
+def test_nb_iv_ig_with_spark_partitions(income_spark, nb_assoc):
+    """The association notebook's stored IV / IG tables (108 values) through the product on the Spark-partitioned table:
+    approxQuantile cutoffs from the merged per-partition sketches, label-class histograms from the binning kernels."""
+    import functools
+    import anovos.data_analyzer.association_evaluator as ae
+    from test_oracle_golden import check_nb_iv_ig
+    check_nb_iv_ig(lambda **kw: ae.IV_calculation(None, income_spark, **kw).toPandas(),
+                   lambda **kw: ae.IG_calculation(None, income_spark, **kw).toPandas(), nb_assoc)
+
+
+def test_nb_quality_checker(income, nb_quality):
+    """Stored outputs of the quality-checker notebook on the income CSV: nullColumns (cells 17-19), IDness (35-37, HLL++
+    default), biasedness (41-43; the mode VALUE only where it is unique - ties are arbitrary in the reference)."""
+    import anovos.data_analyzer.quality_checker as qc
+    calls = {
+        17: (qc.nullColumns_detection, {}), 18: (qc.nullColumns_detection, {"list_of_cols": "all", "drop_cols": ["ifa"]}),
+        19: (qc.nullColumns_detection, {"list_of_cols": ["age", "sex", "race", "workclass", "fnlwgt"]}),
+        35: (qc.IDness_detection, {}), 36: (qc.IDness_detection, {"list_of_cols": "all", "drop_cols": ["ifa"], "treatment_threshold": 0.75}),
+        37: (qc.IDness_detection, {"list_of_cols": ["sex", "race", "workclass"]}),
+        41: (qc.biasedness_detection, {}),
+        42: (qc.biasedness_detection, {"list_of_cols": "all", "drop_cols": ["ifa"], "treatment_threshold": 0.75}),
+        43: (qc.biasedness_detection, {"list_of_cols": ["age", "sex", "race", "workclass", "logfnl"]}),
+    }
+    checked = 0
+    for cell, (fn, kw) in calls.items():
+        _, pr = fn(None, income, **kw)
+        got, exp = frame_by_attr(pr.toPandas()), table_by_attr(nb_quality[cell])
+        assert set(got) == set(exp), (cell, sorted(set(got) ^ set(exp)))
+        for a, row in exp.items():
+            for c, shown in row.items():
+                if c in ("attribute", "mode"):
+                    continue
+                g = got[a][c]
+                assert shown_close(None if pd.isna(g) else g, shown), (cell, a, c, g, shown)
+                checked += 1
+    assert checked > 250
+    _, pr = qc.biasedness_detection(None, income)
+    got, exp = frame_by_attr(pr.toPandas()), table_by_attr(nb_quality[41])
+    same_mode = sum(str(got[a]["mode"]) == exp[a]["mode"] for a in exp)
+    assert same_mode >= len(exp) - 2          # fnlwgt-like ties may differ
+

@@ -5,6 +5,7 @@ import math
 import tempfile
 
 import numpy as np
+import pandas as pd
 import pyarrow as pa
 import pytest
 
@@ -501,3 +502,33 @@ def test_nb_percentiles_exact_with_spark_partitions(income, nb_stats):
     _check_table(O.measures_of_percentiles(t), nb_stats[35], ["min"] + list(S.SUMMARY_PCTS) + ["max"])
     _check_table(O.measures_of_centralTendency(t), nb_stats[17], ["mean", "median", "mode_rows", "mode_pct"])
     _check_table(O.measures_of_dispersion(t), nb_stats[31], ["stddev", "variance", "cov", "IQR", "range"])
+
+
+# ---- the association notebook: IV / IG on the full income CSV (two Spark partitions) --------------------------------------
+
+NB_IV_IG_CALLS = {  # code cell -> kwargs of the call stored in the notebook (label_col="income", event_label=">50K")
+    18: {}, 19: {"drop_cols": ["ifa"]}, 20: {"list_of_cols": ["age", "sex", "race", "workclass", "fnlwgt"]},
+    21: {"list_of_cols": ["age", "sex", "race", "workclass", "fnlwgt"],
+         "encoding_configs": {"bin_method": "equal_range", "bin_size": 10, "monotonicity_check": 0}},
+    22: {"list_of_cols": ["age", "sex", "race", "workclass", "fnlwgt"],
+         "encoding_configs": {"bin_method": "equal_frequency", "bin_size": 20, "monotonicity_check": 0}},
+}
+
+
+def check_nb_iv_ig(iv_fn, ig_fn, nb_assoc):
+    """All stored IV (cells 18-22) and IG (cells 25-29) tables: 54 + 54 values, to the 6 decimals shown.  The numeric
+    attributes hang on approxQuantile(0.01) cutoffs over two merged partition sketches; ifa (an id) has a NULL ig."""
+    n = 0
+    for cell, kw in NB_IV_IG_CALLS.items():
+        for fn, c, col in ((iv_fn, cell, "iv"), (ig_fn, cell + 7, "ig")):
+            got, exp = frame_by_attr(fn(label_col="income", event_label=">50K", **kw)), table_by_attr(nb_assoc[c])
+            assert set(got) == set(exp), (c, sorted(set(got) ^ set(exp)))
+            for a, row in exp.items():
+                assert shown_close(None if pd.isna(got[a][col]) else got[a][col], row[col]), (c, a, got[a][col], row[col])
+                n += 1
+    assert n == 108
+
+
+def test_nb_iv_ig_with_spark_partitions(income_spark, nb_assoc):
+    import functools
+    check_nb_iv_ig(functools.partial(O.IV_calculation, income_spark), functools.partial(O.IG_calculation, income_spark), nb_assoc)
