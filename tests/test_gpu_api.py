@@ -644,6 +644,7 @@ def test_nb_quality_checker(income, nb_quality):
     assert checked > 250
     _, pr = qc.biasedness_detection(None, income)
     got, exp = frame_by_attr(pr.toPandas()), table_by_attr(nb_quality[41])
-    same_mode = sum(str(got[a]["mode"]) == exp[a]["mode"] for a in exp)
-    assert same_mode >= len(exp) - 2          # fnlwgt-like ties may differ
+    same_mode = sum((str(got[a]["mode"]) == exp[a]["mode"]) or (pd.isna(got[a]["mode"]) and exp[a]["mode"] in ("None", "NaN"))
+                    for a in exp)
+    assert same_mode >= len(exp) - 3          # ties (fnlwgt: 13 rows on several values; ifa: every id once) are arbitrary
 
