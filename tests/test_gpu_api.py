@@ -648,3 +648,13 @@ def test_nb_quality_checker(income, nb_quality):
                     for a in exp)
     assert same_mode >= len(exp) - 3          # ties (fnlwgt: 13 rows on several values; ifa: every id once) are arbitrary
 
+
+def test_nb_attribute_binning_head(tr, income_spark):
+    """transformers notebook cells 6 / 8 through the product (the binned frame of a partitioned table is partitioned)."""
+    from test_oracle_golden import NB_BINNING
+    for method, exp in NB_BINNING.items():
+        out = tr.attribute_binning(None, income_spark, list_of_cols=["education-num", "hours-per-week"], method_type=method, bin_size=5)
+        first = next(iter(out.chunks(["education-num", "hours-per-week"])))
+        got = [[int(first.column(c).device()[0][i].item()) for c in ("education-num", "hours-per-week")] for i in range(5)]
+        assert got == exp, (method, got)
+

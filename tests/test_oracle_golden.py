@@ -532,3 +532,19 @@ def check_nb_iv_ig(iv_fn, ig_fn, nb_assoc):
 def test_nb_iv_ig_with_spark_partitions(income_spark, nb_assoc):
     import functools
     check_nb_iv_ig(functools.partial(O.IV_calculation, income_spark), functools.partial(O.IG_calculation, income_spark), nb_assoc)
+
+
+# ---- the transformers notebook: attribute_binning on the income CSV, first five rows as displayed (cells 6 and 8) -------------
+
+NB_BINNING = {   # (education-num, hours-per-week) bin ids of rows 1a..5a
+    "equal_range": [[4, 3], [4, 1], [3, 3], [2, 3], [4, 3]],          # cell 6: bin_size=5, output_mode="append"
+    "equal_frequency": [[4, 2], [4, 1], [1, 2], [1, 2], [4, 2]],      # cell 8: bin_size=5 (approxQuantile over two partitions)
+}
+
+
+def test_nb_attribute_binning_head(income_spark):
+    for method, exp in NB_BINNING.items():
+        out = O.attribute_binning(income_spark, list_of_cols=["education-num", "hours-per-week"], method_type=method, bin_size=5)
+        assert out.column("ifa").slice(0, 5).to_pylist() == ["1a", "2a", "3a", "4a", "5a"]
+        got = [[out.column(c)[i].as_py() for c in ("education-num", "hours-per-week")] for i in range(5)]
+        assert got == exp, (method, got)
