@@ -15,7 +15,7 @@ from collections import OrderedDict
 import numpy as np
 import pandas as pd
 
-from .. import _lib, engine, profile
+from .. import engine
 from ..data_transformer.transformers import compute_cutoffs
 from ..frame import Column, ColumnFrame, as_frame
 from ..result import ResultFrame

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from ..frame import ColumnFrame, as_frame
+from ..frame import ColumnFrame
 from ..result import ResultFrame
 
 

@@ -16,8 +16,6 @@ import os
 import warnings
 from collections import OrderedDict
 
-import numpy as np
-
 from .. import _lib, engine, profile
 from ..frame import Column, ColumnFrame, as_frame
 from ..shared.utils import attributeType_segregation

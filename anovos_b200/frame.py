@@ -11,7 +11,6 @@ torch tensors / numpy arrays.
 """
 from __future__ import annotations
 
-import ctypes as C
 from collections import OrderedDict
 
 import numpy as np

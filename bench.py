@@ -146,11 +146,9 @@ def run_ours(args):
 
 
 def _run_ours(args, out):
-    import numpy as np
     import torch
     import torch.distributed as dist
     from anovos_b200 import engine, frame as framemod, parallel, synth
-    from anovos_b200.frame import ColumnFrame
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -408,7 +406,6 @@ def _run_stream(args, out, wl, rows, cols, world, rank, local):
     resident drift extra.  The chunks are generated on the device inside the timed region (there
     is nowhere to keep them): generation time is measured separately and reported."""
     import tempfile
-    import numpy as np
     import torch
     import torch.distributed as dist
     import anovos.data_analyzer.stats_generator as sg
@@ -574,7 +571,6 @@ def stream_e2e(args, wl, rows, cols, chunk, torch, tmp):
 
 def fused_pass_numbers(src, rows, cols, alg_bytes, peak, torch, engine):
     """anv_moments_hist (the drift target pass: moments + 10-bin histogram in one read)."""
-    import numpy as np
     names = src.columns
     mom = engine.moments(src, names)
     cuts, lohi = [], []
