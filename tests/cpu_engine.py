@@ -1,0 +1,192 @@
+"""TEST INFRASTRUCTURE: a NumPy stand-in for `anovos_b200.engine` so that the product's host layer (argument handling,
+binning models, key alignment of drift, saved artefacts, partition merges, outlier thresholds) can be exercised under
+`-m "not gpu"`.  Every function has the signature and result layout of the engine function it replaces and is written
+from the oracle's primitives; the kernels themselves are tested against the oracle on the GPU (`-m gpu`).
+
+    with cpu_engine.installed():      # monkeypatches engine.*, Column.upload_async and _lib.require_cuda
+        dd.statistics(None, target, source, ...)
+"""
+import contextlib
+
+import numpy as np
+
+from anovos_b200 import _lib, engine, frame as framemod
+from oracle import spark_semantics as S
+
+
+def _values(fr, name):
+    """(float64-or-native values, bool valid) of a HOST-resident column."""
+    col = fr.column(name)
+    vals = np.asarray(col._host)
+    if col._host_valid is None:
+        valid = np.ones(fr.n_rows, dtype=bool)
+    else:
+        bits = np.unpackbits(np.asarray(col._host_valid).view(np.uint8), bitorder="little")
+        valid = bits[:fr.n_rows].astype(bool)
+    return vals[:fr.n_rows], valid
+
+
+def moments(fr, names):
+    if getattr(fr, "is_partitioned", False):
+        return fr.moments(names)
+    out = np.zeros(len(list(names)), dtype=engine._MOM_DT)
+    for i, n in enumerate(names):
+        vals, valid = _values(fr, n)
+        x = vals[valid].astype(np.float64)
+        out[i]["n_valid"], out[i]["n_nonzero"] = x.size, int(np.count_nonzero(x))
+        if x.size:
+            cnt, mean, m2, m3, m4 = S.central_moments(x)
+            out[i]["min"], out[i]["max"], out[i]["mean"] = x.min(), x.max(), mean
+            out[i]["m2"], out[i]["m3"], out[i]["m4"] = m2, m3, m4
+        else:
+            out[i]["min"] = out[i]["max"] = out[i]["mean"] = np.nan
+    return out
+
+
+def histogram(fr, model):
+    if getattr(fr, "is_partitioned", False):
+        return fr.histogram(model)
+    h = np.zeros((len(model.names), model.max_bins + 1), np.uint64)
+    for i, n in enumerate(model.names):
+        vals, valid = _values(fr, n)
+        ids = S.assign_bins(vals.astype(np.float64), valid, model.cutoffs[i], len(model.cutoffs[i]) + 1)
+        h[i, :len(model.cutoffs[i]) + 2] = np.bincount(ids, minlength=len(model.cutoffs[i]) + 2)
+    return h
+
+
+def moments_histogram(fr, model):
+    if getattr(fr, "is_partitioned", False):
+        return fr.moments_histogram(model)
+    return moments(fr, model.names), histogram(fr, model)
+
+
+def code_counts(fr, names):
+    if getattr(fr, "is_partitioned", False):
+        return fr.code_counts(list(names))
+    out = []
+    for n in names:
+        vals, valid = _values(fr, n)
+        card = max(len(fr.column(n).dictionary), 1)
+        h = np.zeros(card + 1, np.uint64)
+        h[0] = int((~valid).sum())
+        h[1:] = np.bincount(vals[valid].astype(np.int64), minlength=card)[:card]
+        out.append(h)
+    return out
+
+
+def drift_reduce(src_counts, tgt_counts, kinds, n_src, n_tgt, src_p=None):
+    n = len(tgt_counts)
+    out = np.zeros(n, dtype=engine._DRIFT_DT)
+    for i in range(n):
+        t = np.asarray(tgt_counts[i], dtype=np.float64)
+        if src_p is None:
+            s = np.asarray(src_counts[i], dtype=np.float64)
+            present_s, p = s > 0, s / n_src
+        else:
+            sp = np.asarray(src_p[i], dtype=np.float64)
+            present_s, p = ~np.isnan(sp), np.nan_to_num(sp)
+        rows = []
+        s_null, t_null = bool(present_s[0]), bool(t[0] > 0)
+        if kinds[i] == 0:
+            if s_null or t_null:
+                rows.append((1e-4, 1e-4))
+        else:
+            rows += [(1e-4, 1e-4)] * (int(s_null) + int(t_null))
+        for k in range(1, len(t)):
+            ps, pt = bool(present_s[k]), bool(t[k] > 0)
+            if ps or pt:
+                rows.append((p[k] if ps else 1e-4, t[k] / n_tgt if pt else 1e-4))
+        psi = hd = pm = qm = cp = cq = ks = 0.0
+        for a, b in rows:
+            a, b = (a or 1e-4), (b or 1e-4)
+            psi += (a - b) * np.log(a / b)
+            hd += (np.sqrt(a) - np.sqrt(b)) ** 2
+            m = (a + b) / 2
+            pm += a * np.log(a / m)
+            qm += b * np.log(b / m)
+            cp += a
+            cq += b
+            ks = max(ks, abs(cp - cq))
+        out[i]["n_rows"] = len(rows)
+        if rows:
+            out[i]["psi"], out[i]["hd"], out[i]["jsd"], out[i]["ks"] = psi, np.sqrt(hd / 2), (pm + qm) / 2, ks
+        else:
+            out[i]["psi"] = out[i]["hd"] = out[i]["jsd"] = out[i]["ks"] = np.nan
+    return out
+
+
+def _sorted_valid(fr, names):
+    """name -> sorted float64 non-null values (chunks of a partitioned frame concatenated)."""
+    names = list(names)
+    if getattr(fr, "is_partitioned", False):
+        parts = {n: [] for n in names}
+        for ch in fr.chunks(names):
+            for n in names:
+                vals, valid = _values(ch, n)
+                parts[n].append(vals[valid].astype(np.float64))
+        return {n: np.sort(np.concatenate(parts[n])) if parts[n] else np.zeros(0) for n in names}
+    return {n: np.sort(_values(fr, n)[0][_values(fr, n)[1]].astype(np.float64)) for n in names}
+
+
+def select_ranks(fr, names, ranks):
+    names = list(names)
+    whole = _sorted_valid(fr, names)
+    ranks = np.asarray(ranks, dtype=np.int64).reshape(len(names), -1)
+    out = np.full(ranks.shape, np.nan)
+    for i, n in enumerate(names):
+        for j, r in enumerate(ranks[i]):
+            if r > 0:
+                out[i, j] = whole[n][r - 1]
+    return out
+
+
+def sort_mode_distinct(fr, names, ranks=None):
+    names = list(names)
+    whole = _sorted_valid(fr, names)
+    res = []
+    for n in names:
+        x = whole[n] + 0.0
+        if x.size == 0:
+            res.append((None, None, 0))
+            continue
+        u, k = np.unique(x, return_counts=True)
+        res.append((float(u[np.argmax(k)]), int(k.max()), int(u.size)))
+    if ranks is None:
+        return res
+    return res, select_ranks(fr, names, ranks)
+
+
+def hll_registers(fr, names, p):
+    if getattr(fr, "is_partitioned", False):
+        return fr.hll_registers(list(names), p)
+    out = np.zeros((len(list(names)), 1 << p), np.uint32)
+    for i, n in enumerate(names):
+        vals, valid = _values(fr, n)
+        out[i] = S.hll_registers(S.hll_hashes(vals[valid], fr.column(n).sdtype), p)
+    return out
+
+
+class _Torch:
+    """What the host layer asks of torch when no kernel runs: a stream object for the chunk prefetcher."""
+    class cuda:
+        @staticmethod
+        def Stream():
+            return None
+
+
+@contextlib.contextmanager
+def installed():
+    names = ["moments", "histogram", "moments_histogram", "code_counts", "drift_reduce", "select_ranks", "sort_mode_distinct",
+             "hll_registers"]
+    saved = {n: getattr(engine, n) for n in names}
+    saved_req, saved_up = _lib.require_cuda, framemod.Column.upload_async
+    try:
+        for n in names:
+            setattr(engine, n, globals()[n])
+        _lib.require_cuda = lambda: _Torch
+        framemod.Column.upload_async = lambda self, stream: None
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(engine, n, f)
+        _lib.require_cuda, framemod.Column.upload_async = saved_req, saved_up

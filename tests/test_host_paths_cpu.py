@@ -1,0 +1,118 @@
+"""Host paths of the product under `-m "not gpu"`: the NumPy engine stand-in of tests/cpu_engine.py replaces the kernels, so
+drift (key alignment, saved model / frequency files, flags), outlier thresholds, Spark-partitioned percentiles and the
+row-partition merges run end to end on CPU and are compared with the oracle and with the reference's pins."""
+import json
+import os
+import warnings
+
+import numpy as np
+import pandas as pd
+import pyarrow as pa
+import pytest
+
+import cpu_engine
+from golden_util import frame_by_attr, shown_close, table_by_attr
+from oracle import api as O
+from oracle import spark_semantics as S
+
+
+def _close_cols(a, b, cols, rtol=1e-9):
+    for c in cols:
+        assert np.allclose(np.asarray(a[c], float), np.asarray(b[c], float), rtol=rtol, atol=1e-15, equal_nan=True), c
+
+
+def _drift_tables():
+    rng = np.random.default_rng(4)
+    n = 12_007
+    def mk(shift, seed):
+        r = np.random.default_rng(seed)
+        return pa.table({
+            "x": pa.array(r.normal(shift, 2, n).astype(np.float32), mask=r.random(n) < 0.03),
+            "k": pa.array(r.integers(0, 40, n).astype(np.int64)),
+            "all_null": pa.array([None] * n, pa.float64()),
+            "s": pa.array(r.choice(["a", "b", "c", "dd", "e,f"], n, p=[0.4, 0.3, 0.2, 0.05, 0.05]), mask=r.random(n) < 0.1),
+            "wide": pa.array(["k%04d" % v for v in r.integers(0, 300, n)]),
+        })
+    return mk(0.0, 1), mk(0.4, 2)
+
+
+@pytest.mark.parametrize("bin_method", ["equal_range", "equal_frequency"])
+def test_drift_host_path_equals_oracle(bin_method, tmp_path):
+    import anovos.drift_stability.drift_detector as dd
+    src, tgt = _drift_tables()
+    kw = dict(method_type="all", use_sampling=False, bin_method=bin_method, bin_size=8)
+    with cpu_engine.installed(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # equal_range drops the all-null column with a warning
+        got = dd.statistics(None, tgt, src, source_path=str(tmp_path / "p"), **kw).toPandas()
+        again = dd.statistics(None, tgt, None, pre_existing_source=True, source_path=str(tmp_path / "p"), **kw).toPandas()
+        exp = O.statistics(tgt, src, source_path=str(tmp_path / "o"), **kw)
+    assert got["attribute"].tolist() == exp["attribute"].tolist() and got["flagged"].tolist() == exp["flagged"].tolist()
+    _close_cols(got, exp, ["PSI", "HD", "JSD", "KS"])
+    _close_cols(again, exp, ["PSI", "HD", "JSD", "KS"], rtol=1e-9)     # the saved model + frequency CSVs round-trip
+    # artefacts in the reference's layout
+    assert os.path.isdir(tmp_path / "p" / "drift_statistics" / "attribute_binning")
+    f = pd.read_csv(tmp_path / "p" / "drift_statistics" / "frequency_counts" / "s" / "part-00000.csv")
+    assert list(f.columns) == ["s", "p"] and abs(f["p"].sum() - (1 - src.column("s").null_count / src.num_rows)) < 1e-12
+
+
+def test_nb_drift_and_percentiles_through_the_host_path(income, income_source, income_spark, nb_drift, nb_stats, tmp_path):
+    """Notebook pins through the PRODUCT's host code on CPU: the 21-column PSI table and - with Spark's partitioning -
+    all 81 summary() percentiles (per-partition sketch samples merged by shared/gk.py)."""
+    import anovos.data_analyzer.stats_generator as sg
+    import anovos.drift_stability.drift_detector as dd
+    with cpu_engine.installed():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            d = dd.statistics(None, income, income_source, method_type="PSI", use_sampling=False, source_path=str(tmp_path)).toPandas()
+        pct = sg.measures_of_percentiles(None, income_spark).toPandas()
+        cen = sg.measures_of_centralTendency(None, income_spark).toPandas()
+    psi_tables = [t for t in nb_drift.values() if t["columns"][:2] == ["attribute", "PSI"] and len(t["rows"]) >= 20]
+    exp = table_by_attr(psi_tables[0])
+    got = frame_by_attr(d)
+    assert sum(shown_close(got[a]["PSI"], r["PSI"]) for a, r in exp.items() if a in got) >= len(exp) - 1
+    exp = table_by_attr(nb_stats[35])
+    got = frame_by_attr(pct)
+    for a, row in exp.items():
+        for c in ["min", "max"] + list(S.SUMMARY_PCTS):
+            g = got[a][c]
+            assert shown_close(None if pd.isna(g) else g, row[c]), (a, c, g, row[c])
+    exp, got = table_by_attr(nb_stats[17]), frame_by_attr(cen)
+    for a, row in exp.items():
+        g = got[a]["median"]
+        assert shown_close(None if pd.isna(g) else g, row["median"]), (a, g, row["median"])
+
+
+def test_outlier_thresholds_and_counts_host_path(income_part0):
+    """The 13 reference pins of test_quality_checker.py:526-637 that do not need a treated frame: thresholds from
+    approxQuantile ranks / moments, counts from the compare pass, skew exclusion, saved-model round trip."""
+    import anovos.data_analyzer.quality_checker as qc
+    from test_oracle_golden import OUTLIER_PINS_UPPER
+    t = income_part0.append_column("label", pa.array([0] * income_part0.num_rows))
+    with cpu_engine.installed(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # capital-loss is excluded as skewed, with a warning
+        _, pr = qc.outlier_detection(None, t, drop_cols=["ifa", "label"], treatment=False, print_impact=True)
+    got = {r["attribute"]: [r["lower_outliers"], r["upper_outliers"], r["excluded_due_to_skewness"]] for r in pr.toPandas().to_dict("records")}
+    assert got == OUTLIER_PINS_UPPER
+    with cpu_engine.installed():
+        _, pr = qc.outlier_detection(None, t, list_of_cols=["age", "education-num"], detection_side="both",
+                                     detection_configs={"pctile_lower": 0.02, "pctile_upper": 0.98}, treatment=False, print_impact=True)
+    got = {r["attribute"]: [r["lower_outliers"], r["upper_outliers"]] for r in pr.toPandas().to_dict("records")}
+    assert got == {"age": [202, 482], "education-num": [267, 205]}
+
+
+def test_row_partition_merges_host_path(income):
+    """PartitionedFrame on CPU: chunked moments / histograms / code counts / HLL registers / percentiles == the whole frame."""
+    import anovos.data_analyzer.stats_generator as sg
+    from anovos_b200.frame import ColumnFrame
+    from anovos_b200.partitioned import PartitionedFrame
+    with cpu_engine.installed():
+        whole = ColumnFrame.from_arrow(income)
+        parts = PartitionedFrame.from_frame(income, 4096)
+        assert parts.n_chunks == 8 and parts.count() == income.num_rows
+        for fn in ("measures_of_counts", "measures_of_percentiles", "measures_of_cardinality", "measures_of_centralTendency"):
+            a, b = getattr(sg, fn)(None, whole).toPandas(), getattr(sg, fn)(None, parts).toPandas()
+            assert a.equals(b), fn
+        for fn in ("measures_of_dispersion", "measures_of_shape"):
+            a, b = getattr(sg, fn)(None, whole).toPandas(), getattr(sg, fn)(None, parts).toPandas()
+            assert np.allclose(a.drop(columns="attribute").to_numpy(float), b.drop(columns="attribute").to_numpy(float),
+                               rtol=1e-9, atol=1.01e-4, equal_nan=True), fn
