@@ -116,3 +116,46 @@ def test_row_partition_merges_host_path(income):
             a, b = getattr(sg, fn)(None, whole).toPandas(), getattr(sg, fn)(None, parts).toPandas()
             assert np.allclose(a.drop(columns="attribute").to_numpy(float), b.drop(columns="attribute").to_numpy(float),
                                rtol=1e-9, atol=1.01e-4, equal_nan=True), fn
+
+
+def test_stability_index_host_path(nb_drift, tmp_path):
+    """stability_index_computation (test_stability.py:69-92 and notebook cells 14-17): K1 per dataset comes from the
+    stand-in, the CV / score / weighting arithmetic and the metric files are the product's."""
+    import anovos.drift_stability.stability as st
+    from test_oracle_golden import _stab_tables, check_stability_notebook
+    with cpu_engine.installed():
+        r = st.stability_index_computation(None, _stab_tables()).toPandas().iloc[0]
+        np.testing.assert_almost_equal([r[c] for c in ("mean_cv", "stddev_cv", "kurtosis_cv", "mean_si", "stddev_si", "kurtosis_si",
+                                                       "stability_index", "flagged")], [0.162, 0.62, 0.198, 2.0, 0.0, 2.0, 1.4, 0.0], 3)
+        with pytest.raises(ValueError):
+            st.stability_index_computation(None, _stab_tables(), metric_weightages={"mean": 0.5})
+        check_stability_notebook(lambda tables, **kw: st.stability_index_computation(None, tables, **kw).toPandas(), nb_drift, tmp_path)
+
+
+def test_quality_checker_notebook_host_path(income, nb_quality):
+    """nullColumns / IDness (HLL++ default) / biasedness tables of the quality-checker notebook through the product's
+    host code (cells 17-19, 35-37, 41-43)."""
+    import anovos.data_analyzer.quality_checker as qc
+    calls = {
+        17: (qc.nullColumns_detection, {}), 18: (qc.nullColumns_detection, {"list_of_cols": "all", "drop_cols": ["ifa"]}),
+        19: (qc.nullColumns_detection, {"list_of_cols": ["age", "sex", "race", "workclass", "fnlwgt"]}),
+        35: (qc.IDness_detection, {}), 36: (qc.IDness_detection, {"list_of_cols": "all", "drop_cols": ["ifa"], "treatment_threshold": 0.75}),
+        37: (qc.IDness_detection, {"list_of_cols": ["sex", "race", "workclass"]}),
+        41: (qc.biasedness_detection, {}),
+        42: (qc.biasedness_detection, {"list_of_cols": "all", "drop_cols": ["ifa"], "treatment_threshold": 0.75}),
+        43: (qc.biasedness_detection, {"list_of_cols": ["age", "sex", "race", "workclass", "logfnl"]}),
+    }
+    checked = 0
+    with cpu_engine.installed():
+        for cell, (fn, kw) in calls.items():
+            _, pr = fn(None, income, **kw)
+            got, exp = frame_by_attr(pr.toPandas()), table_by_attr(nb_quality[cell])
+            assert set(got) == set(exp), (cell, sorted(set(got) ^ set(exp)))
+            for a, row in exp.items():
+                for c, shown in row.items():
+                    if c in ("attribute", "mode"):
+                        continue
+                    g = got[a][c]
+                    assert shown_close(None if pd.isna(g) else g, shown), (cell, a, c, g, shown)
+                    checked += 1
+    assert checked > 250
