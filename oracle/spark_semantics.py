@@ -7,9 +7,10 @@ Reference call sites (relative to /root/reference/src/main/anovos):
   data_analyzer/stats_generator.py:163,241,310,488,607,611,813,908,993
   data_transformer/transformers.py:215,219,248-271
   drift_stability/drift_detector.py:253-334
-Pins: src/test/anovos/data_analyzer/test_stats_generator.py,
-src/test/anovos/drift_stability/test_drift_detector.py and the stored outputs of
-examples/notebooks/{data_analyzer__stats_generator,drift_stability}.ipynb.
+Pins: src/test/anovos/data_analyzer/{test_stats_generator,test_quality_checker,test_association_evaluator}.py,
+src/test/anovos/drift_stability/{test_drift_detector,test_stability}.py and the stored outputs of
+examples/notebooks/{data_analyzer__stats_generator,data_analyzer__quality_checker,data_analyzer__association_evaluator,
+data_transformer__transformers,drift_stability}.ipynb.
 """
 from __future__ import annotations
 
