@@ -3,7 +3,7 @@ binning models, key alignment of drift, saved artefacts, partition merges, outli
 `-m "not gpu"`.  Every function has the signature and result layout of the engine function it replaces and is written
 from the oracle's primitives; the kernels themselves are tested against the oracle on the GPU (`-m gpu`).
 
-    with cpu_engine.installed():      # monkeypatches engine.*, Column.upload_async and _lib.require_cuda
+    with cpu_engine.installed():      # monkeypatches engine.*, Column.device / upload_async and _lib.require_cuda
         dd.statistics(None, target, source, ...)
 """
 import contextlib
@@ -166,27 +166,60 @@ def hll_registers(fr, names, p):
     return out
 
 
-class _Torch:
-    """What the host layer asks of torch when no kernel runs: a stream object for the chunk prefetcher."""
-    class cuda:
-        @staticmethod
-        def Stream():
-            return None
+def bin_assign(fr, model):
+    """-> int32 torch (CPU) tensor [n_cols, n_rows] of bin ids, 0 = null row (the layout anv_bin_assign fills)."""
+    import torch
+    out = np.zeros((max(len(model.names), 1), fr.n_rows), np.int32)
+    for i, n in enumerate(model.names):
+        vals, valid = _values(fr, n)
+        out[i] = S.assign_bins(vals.astype(np.float64), valid, model.cutoffs[i], len(model.cutoffs[i]) + 1)
+    return torch.from_numpy(out)[:len(model.names)]
+
+
+class _Cuda:
+    @staticmethod
+    def Stream():
+        return None
+
+
+class _TorchProxy:
+    """What the host layer asks of torch when no kernel runs: tensor ops on the CPU, and a stream object for the chunk
+    prefetcher (uploads are no-ops here)."""
+    cuda = _Cuda
+
+    def __getattr__(self, name):
+        import torch
+        return getattr(torch, name)
+
+
+def _host_device(self):
+    """Column.device() without a GPU: the host arrays as CPU tensors."""
+    import torch
+    if self.kind == "other":
+        raise _lib.AnvError("column %r has dtype %s which the hot path does not process" % (self.name, self.sdtype))
+    if self._dev is None:
+        h = np.ascontiguousarray(self._host)
+        self._dev = torch.from_numpy(h.copy() if not h.flags.writeable else h)
+        if self._host_valid is not None:
+            self._dev_valid = torch.from_numpy(np.ascontiguousarray(self._host_valid).copy())
+    return self._dev, self._dev_valid
 
 
 @contextlib.contextmanager
 def installed():
     names = ["moments", "histogram", "moments_histogram", "code_counts", "drift_reduce", "select_ranks", "sort_mode_distinct",
-             "hll_registers"]
+             "hll_registers", "bin_assign"]
     saved = {n: getattr(engine, n) for n in names}
-    saved_req, saved_up = _lib.require_cuda, framemod.Column.upload_async
+    saved_req, saved_up, saved_dev = _lib.require_cuda, framemod.Column.upload_async, framemod.Column.device
     try:
         for n in names:
             setattr(engine, n, globals()[n])
-        _lib.require_cuda = lambda: _Torch
+        proxy = _TorchProxy()
+        _lib.require_cuda = lambda: proxy
         framemod.Column.upload_async = lambda self, stream: None
+        framemod.Column.device = _host_device
         yield
     finally:
         for n, f in saved.items():
             setattr(engine, n, f)
-        _lib.require_cuda, framemod.Column.upload_async = saved_req, saved_up
+        _lib.require_cuda, framemod.Column.upload_async, framemod.Column.device = saved_req, saved_up, saved_dev

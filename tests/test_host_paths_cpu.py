@@ -159,3 +159,45 @@ def test_quality_checker_notebook_host_path(income, nb_quality):
                     assert shown_close(None if pd.isna(g) else g, shown), (cell, a, c, g, shown)
                     checked += 1
     assert checked > 250
+
+
+def test_attribute_binning_host_path(income_part1, tmp_path):
+    """data_transformer/test_transformers.py:37-104 with the reference's inputs and checks, plus ids == oracle for both
+    methods, the saved-model round trip, categorical labels and the append mode."""
+    import anovos.data_transformer.transformers as tr
+    cols = ["age", "fnlwgt", "hours-per-week"]
+
+    def ids(fr, c):
+        d, v = fr.column(c).device()
+        return np.asarray(d), v
+
+    with cpu_engine.installed():
+        out = tr.attribute_binning(None, income_part1, list_of_cols=cols, bin_size=20, model_path=str(tmp_path))
+        assert len(out.columns) == 17
+        for c in cols:
+            d, v = ids(out, c)
+            valid = np.asarray(income_part1.column(c).is_valid())
+            assert d[valid].min() == 1 and d[valid].max() == 20
+        with pytest.raises(IndexError, match="list index out of range"):
+            tr.attribute_binning(None, income_part1, list_of_cols=["education-num"], bin_size=20, pre_existing_model=True,
+                                 model_path=str(tmp_path))
+        same = tr.attribute_binning(None, income_part1, list_of_cols=[], bin_size=20)
+        assert same.columns == income_part1.column_names
+        app = tr.attribute_binning(None, income_part1, list_of_cols=cols, bin_size=20, output_mode="append")
+        assert len(app.columns) == 20 and app.columns[-3:] == [c + "_binned" for c in cols]
+        for method in ("equal_range", "equal_frequency"):
+            got = tr.attribute_binning(None, income_part1, list_of_cols=cols, method_type=method, bin_size=7)
+            exp = O.attribute_binning(income_part1, list_of_cols=cols, method_type=method, bin_size=7)
+            for c in cols:
+                d, _ = ids(got, c)
+                e = np.asarray(exp.column(c).fill_null(0))
+                assert np.array_equal(d, e), (method, c)
+        again = tr.attribute_binning(None, income_part1, list_of_cols=cols, pre_existing_model=True, model_path=str(tmp_path))
+        for c in cols:
+            assert np.array_equal(ids(again, c)[0], ids(out, c)[0])
+        lab = tr.attribute_binning(None, income_part1, list_of_cols=["age"], bin_size=4, bin_dtype="categorical")
+        assert lab.column("age").kind == "cat" and len(lab.column("age").dictionary) == 4
+        assert lab.column("age").dictionary[0].startswith("<= ") and lab.column("age").dictionary[-1].startswith("> ")
+        for bad in (dict(bin_size=1), dict(method_type="foo"), dict(output_mode="x"), dict(list_of_cols=["workclass"])):
+            with pytest.raises(TypeError):
+                tr.attribute_binning(None, income_part1, **{"list_of_cols": cols, **bad})
