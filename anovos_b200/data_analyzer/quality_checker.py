@@ -381,11 +381,11 @@ def outlier_detection(spark, idf, list_of_cols="all", drop_cols=[], detection_si
                                           "(detection with print_impact=True is)")
             hist = engine.histogram(fr, model)
         new_cols = OrderedDict((n, fr.column(n)) for n in fr.columns)
-        keep = torch.ones(fr.n_rows, dtype=torch.bool, device="cuda") if need_rows else None
+        keep = torch.ones(fr.n_rows, dtype=torch.bool, device=ids.device) if need_rows else None
         for i, c in enumerate(cols):
             flags_of_bin = specs[i][1]
             if need_rows:
-                flag = torch.zeros(fr.n_rows, dtype=torch.int8, device="cuda")
+                flag = torch.zeros(fr.n_rows, dtype=torch.int8, device=ids.device)
                 for b, f in enumerate(flags_of_bin, start=1):
                     if f:
                         flag[ids[i] == b] = f
@@ -403,9 +403,9 @@ def outlier_detection(spark, idf, list_of_cols="all", drop_cols=[], detection_si
                 lo, hi = params[i]
                 out = d.to(torch.float64)
                 if lo is not None:
-                    out = torch.where(flag == -1, torch.tensor(float(lo), dtype=torch.float64, device="cuda"), out)
+                    out = torch.where(flag == -1, torch.tensor(float(lo), dtype=torch.float64, device=out.device), out)
                 if hi is not None:
-                    out = torch.where(flag == 1, torch.tensor(float(hi), dtype=torch.float64, device="cuda"), out)
+                    out = torch.where(flag == 1, torch.tensor(float(hi), dtype=torch.float64, device=out.device), out)
                 new_cols[name] = Column(name, "double", fr.n_rows, dev=out, dev_valid=v, anv_dtype=_lib.ANV_F64,
                                         null_count=src.null_count)
             elif treatment_method == "null_replacement":

@@ -222,8 +222,8 @@ class ColumnFrame:
         torch = _lib.require_cuda()
         d, v = self._cols[name].device()
         if v is None:
-            return torch.ones(self.n_rows, dtype=torch.bool, device="cuda")
-        rows = torch.arange(self.n_rows, device="cuda")
+            return torch.ones(self.n_rows, dtype=torch.bool, device=d.device)
+        rows = torch.arange(self.n_rows, device=d.device)
         return ((v[rows >> 5] >> (rows & 31).to(torch.int32)) & 1).bool()
 
     def filter_rows(self, keep) -> "ColumnFrame":
@@ -251,11 +251,12 @@ class ColumnFrame:
         """`idf.dropna(subset=cols)`: keep the rows whose `subset` columns are all non-null."""
         torch = _lib.require_cuda()
         subset = list(subset) if subset is not None else self.columns
-        keep = torch.ones(self.n_rows, dtype=torch.bool, device="cuda")
+        keep = None
         for n in subset:
             if self._cols[n].kind != "other" and self._cols[n].device()[1] is not None:
-                keep &= self.valid_mask(n)
-        return self.filter_rows(keep)
+                m = self.valid_mask(n)
+                keep = m if keep is None else keep & m
+        return self if keep is None else self.filter_rows(keep)
 
     def slice_rows(self, r0: int, r1: int) -> "ColumnFrame":
         """Zero-copy view of rows [r0, r1): r0 must be a multiple of 32 so that the validity

@@ -17,11 +17,15 @@ from oracle import spark_semantics as S
 def _values(fr, name):
     """(float64-or-native values, bool valid) of a HOST-resident column."""
     col = fr.column(name)
-    vals = np.asarray(col._host)
-    if col._host_valid is None:
+    if col._host is not None:
+        vals, words = np.asarray(col._host), col._host_valid
+    else:                                  # a column produced by a frame transform: CPU tensors under this stand-in
+        vals = col._dev.numpy()
+        words = None if col._dev_valid is None else col._dev_valid.numpy()
+    if words is None:
         valid = np.ones(fr.n_rows, dtype=bool)
     else:
-        bits = np.unpackbits(np.asarray(col._host_valid).view(np.uint8), bitorder="little")
+        bits = np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")
         valid = bits[:fr.n_rows].astype(bool)
     return vals[:fr.n_rows], valid
 

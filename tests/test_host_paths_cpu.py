@@ -201,3 +201,28 @@ def test_attribute_binning_host_path(income_part1, tmp_path):
         for bad in (dict(bin_size=1), dict(method_type="foo"), dict(output_mode="x"), dict(list_of_cols=["workclass"])):
             with pytest.raises(TypeError):
                 tr.attribute_binning(None, income_part1, **{"list_of_cols": cols, **bad})
+
+
+def test_outlier_treatments_host_path(income_part0, tmp_path):
+    """All four reference outlier tests (test_quality_checker.py:526-668) incl. the treated frames - row removal, value
+    replacement (clamped min / max), null replacement with a saved model - through the product's host code; the per-row
+    compare comes from the stand-in's bin ids, the treated columns from the product's tensor ops (CPU tensors here)."""
+    import anovos.data_analyzer.quality_checker as qc
+    from anovos_b200 import engine
+    from test_oracle_golden import check_outlier_reference_tests
+
+    def view(odf):
+        def minmax(c):
+            m = engine.moments(odf, [c])[0]
+            return (m["min"], m["max"])
+        return {"rows": odf.count(), "columns": odf.columns, "minmax": minmax,
+                "nulls": lambda c: odf.count() - int(engine.moments(odf, [c])[0]["n_valid"])}
+
+    def run(table, print_impact=False, **kw):
+        r = qc.outlier_detection(None, table, print_impact=print_impact, **kw)
+        return (view(r[0]), r[1].toPandas()) if print_impact else view(r)
+
+    t = income_part0.append_column("label", pa.array([0] * income_part0.num_rows))
+    with cpu_engine.installed(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        check_outlier_reference_tests(run, t, tmp_path)
