@@ -61,7 +61,7 @@ def _label_bitmaps(fr: ColumnFrame, label_col, event_label):
         is_ev = d == code
     else:
         is_ev = d.to(torch.float64) == float(event_label)
-    valid = _unpack_bits(v, fr.n_rows) if v is not None else torch.ones(fr.n_rows, dtype=torch.bool, device="cuda")
+    valid = _unpack_bits(v, fr.n_rows) if v is not None else torch.ones(fr.n_rows, dtype=torch.bool, device=d.device)
     ev, nev = is_ev & valid, (~is_ev) & valid
     return _pack_bits(ev), _pack_bits(nev), int(ev.sum().item())
 

@@ -226,3 +226,20 @@ def test_outlier_treatments_host_path(income_part0, tmp_path):
     with cpu_engine.installed(), warnings.catch_warnings():
         warnings.simplefilter("ignore")
         check_outlier_reference_tests(run, t, tmp_path)
+
+
+def test_iv_ig_host_path(income_part0, income_spark, nb_assoc):
+    """IV / IG through the product's host code: the unit-test pins of test_association_evaluator.py:49-240 (single parquet
+    file) and the 108 stored notebook values (income CSV with Spark's two scan partitions)."""
+    import functools
+    import anovos.data_analyzer.association_evaluator as ae
+    from test_oracle_golden import check_iv_ig, check_nb_iv_ig, label_table
+    with cpu_engine.installed():
+        t = label_table(income_part0)
+        check_iv_ig(ae.IV_calculation(None, t, drop_cols=["ifa"]).toPandas(), ae.IG_calculation(None, t, drop_cols=["ifa"]).toPandas())
+        check_nb_iv_ig(lambda **kw: ae.IV_calculation(None, income_spark, **kw).toPandas(),
+                       lambda **kw: ae.IG_calculation(None, income_spark, **kw).toPandas(), nb_assoc)
+        with pytest.raises(TypeError):
+            ae.IV_calculation(None, t, label_col="nope")
+        with pytest.raises(TypeError):
+            ae.IV_calculation(None, t, event_label=7)
