@@ -198,8 +198,25 @@ class ColumnProfile:
         return int(np.unique(x).size)
 
 
+_PROFILE_LRU = []   # [(table, {name: ColumnProfile})], most recent last: pyarrow Tables are immutable, so a profile
+_PROFILE_LRU_SIZE = 3  # (values, float64 image, sorted copy) can be shared by the functions called on the same table
+
+
 def _profiles(table, cols):
-    return {c: ColumnProfile(table, c) for c in cols}
+    """ColumnProfiles of `cols`, memoised per table OBJECT (the scale tests call ten functions on one 10M-row table:
+    one sort per column instead of one per function).  Strong references keep id() stable."""
+    for i, (t, d) in enumerate(_PROFILE_LRU):
+        if t is table:
+            _PROFILE_LRU.append(_PROFILE_LRU.pop(i))
+            break
+    else:
+        d = {}
+        _PROFILE_LRU.append((table, d))
+        del _PROFILE_LRU[:-_PROFILE_LRU_SIZE]
+    for c in cols:
+        if c not in d:
+            d[c] = ColumnProfile(table, c)
+    return {c: d[c] for c in cols}
 
 
 # ---------------------------------------------------------------------------
@@ -427,7 +444,7 @@ def binning_cutoffs(table, cols, method_type="equal_range", bin_size=10):
     """-> (kept cols, cutoffs list-of-lists) following transformers.py:210-240."""
     kept, cuts, dropped = [], [], []
     for c in cols:
-        p = ColumnProfile(table, c)
+        p = _profiles(table, [c])[c]
         if method_type == "equal_frequency":
             if p.n == 0:
                 kept.append(c)
@@ -490,7 +507,7 @@ def attribute_binning(table, list_of_cols="all", drop_cols=[], method_type="equa
     out = table
     n_over = (len(cuts[0]) + 1) if cuts else bin_size            # :269 quirk (Appendix C #3)
     for c, cut in zip(cols, cuts):
-        p = ColumnProfile(table, c)
+        p = _profiles(table, [c])[c]
         x = p.values.astype(np.float64)
         ids = S.assign_bins(x, p.valid, cut, bin_size)
         ids[(ids == len(cut) + 1)] = n_over

@@ -622,7 +622,8 @@ def hll_precision(rsd) -> int:
 def hll_hashes(values: np.ndarray, sdtype: str) -> np.ndarray:
     """Spark's per-type XXH64 encoding of non-null values -> uint64 hashes."""
     if sdtype == "string":
-        return np.array([xxh64_bytes(str(s).encode("utf-8")) for s in values], dtype=np.uint64)
+        # the registers are a max over the values: hashing every DISTINCT string once gives the same registers
+        return np.array([xxh64_bytes(str(s).encode("utf-8")) for s in set(values.tolist())], dtype=np.uint64)
     if sdtype == "int":
         return xxh64_int_np(values.astype(np.int32))
     if sdtype in ("bigint", "long"):

@@ -13,7 +13,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from golden_util import cell_value, frame_by_attr, shown_close, table_by_attr
+from golden_util import assert_frames_match, cell_value, frame_by_attr, shown_close, table_by_attr
 from oracle import api as O
 from oracle import spark_semantics as S
 
@@ -354,22 +354,8 @@ def _synth(n, seed, shift=False):
     return pa.table(cols)
 
 
-def _cmp_frames(got, exp, tol=1e-4):
-    got, exp = got.toPandas(), exp
-    assert got["attribute"].tolist() == exp["attribute"].tolist()
-    for c in exp.columns:
-        if c == "attribute":
-            continue
-        for a, g, e in zip(exp["attribute"], got[c].tolist(), exp[c].tolist()):
-            g_none = g is None or (isinstance(g, float) and math.isnan(g))
-            e_none = e is None or (isinstance(e, float) and math.isnan(e))
-            if g_none or e_none:
-                assert g_none and e_none, (a, c, g, e)
-            elif isinstance(e, str):
-                assert g == e, (a, c, g, e)
-            else:
-                assert abs(float(g) - float(e)) <= tol * max(1.0, abs(float(e))) * 1.0001e-0 * 1e-0 if tol < 1e-4 else \
-                    abs(float(g) - float(e)) <= 1.0001e-4 * max(1.0, abs(float(e)) * 1e-2), (a, c, g, e)
+def _cmp_frames(got, exp):
+    assert_frames_match(got.toPandas(), exp)
 
 
 @pytest.mark.parametrize("n", [37, 20011, 400003])
