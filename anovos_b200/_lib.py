@@ -43,6 +43,7 @@ _lib = None
 _P, _I, _L, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 _SIGNATURES = {
     "anv_version": (C.c_int, []),
+    "anv_source_hash": (C.c_char_p, []),
     "anv_last_error": (C.c_char_p, []),
     "anv_device_info": (C.c_int, [_P, _P, _P, _P]),
     "anv_moments_workspace_bytes": (_SZ, [_I, _L]),
@@ -85,6 +86,14 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             f = getattr(h, name)
             f.restype, f.argtypes = res, args
+        if not os.environ.get("ANOVOS_B200_LIB"):
+            # a stale binary (built from older .cu sources) would load silently and its struct layouts / workspace
+            # sizing could have drifted from this binding: compare the source hash baked into the .so
+            from . import build as _build
+            want, have = _build.source_hash(), h.anv_source_hash().decode()
+            if have != want:
+                raise AnvError("libanovos_b200.so is stale: built from sources %s, the tree holds %s. Run "
+                               "`python -m anovos_b200.build`." % (have[:12], want[:12]))
         _lib = h
     return _lib
 

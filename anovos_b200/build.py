@@ -23,6 +23,18 @@ def _nvcc():
     return "nvcc"
 
 
+def source_hash():
+    """sha1 over every kernel source + the public header, in name order."""
+    import hashlib
+    h = hashlib.sha1()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "anovos_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -54,12 +66,20 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "anovos_b200.h"))
     objs, procs = [], []
+    digest = source_hash()
+    stamp = os.path.join(objdir, "source_hash.txt")
+    old_digest = open(stamp).read().strip() if os.path.exists(stamp) else ""
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
-        if force or _stale(obj, [src] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        extra = []
+        stale = force or _stale(obj, [src] + headers)
+        if s == "capi.cu":      # carries the hash of ALL sources: recompiled (cheap) whenever any of them changed
+            extra = ['-DANV_SOURCE_HASH="%s"' % digest]
+            stale = stale or digest != old_digest
+        if stale:
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
             log = open(obj + ".log", "w")
             procs.append((s, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT), obj + ".log"))
     failed = False
@@ -74,6 +94,8 @@ def build(force=False, verbose=False):
     if force or procs or _stale(LIB, objs):
         cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         subprocess.check_call(cmd)
+    with open(stamp, "w") as f:
+        f.write(digest)
     return LIB
 
 

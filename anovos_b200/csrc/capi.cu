@@ -20,6 +20,12 @@ int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace anv
 
 extern "C" int anv_version(void) { return ANV_VERSION; }
+#ifndef ANV_SOURCE_HASH
+#define ANV_SOURCE_HASH "unknown"
+#endif
+// sha1 over the .cu / .cuh sources + include/anovos_b200.h this binary was built from (anovos_b200/build.py): the Python
+// binding refuses a stale .so whose struct layouts or workspace sizing may have drifted from the sources next to it.
+extern "C" const char* anv_source_hash(void) { return ANV_SOURCE_HASH; }
 extern "C" const char* anv_last_error(void) { return anv::g_err; }
 
 extern "C" int anv_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {

@@ -74,10 +74,15 @@ def _utf8_sorted(fr, col):
     return fr._cache[key]
 
 
-def _load_frequency(model_path, col):
+def _load_frequency(model_path, col, string_keys=False):
+    """The saved [<col>, p] table of a source column (:245-250).  Keys of string columns are read back as the strings
+    that were written: Spark's CSV reader treats only the EMPTY field as null, so categories spelled "NA", "null",
+    "None", "nan" ... stay categories and "00501" / "1.0" keep their spelling (pandas' defaults would turn the former
+    into NaN and re-type the latter, silently changing the join with the target's keys).  Bin ids stay integers."""
     d = _freq_dir(model_path, col)
     files = sorted(f for f in os.listdir(d) if f.endswith(".csv"))
-    return pd.concat([pd.read_csv(os.path.join(d, f), keep_default_na=True) for f in files], ignore_index=True)
+    kw = dict(dtype={col: str}, keep_default_na=False, na_values={col: [""]}) if string_keys else {}
+    return pd.concat([pd.read_csv(os.path.join(d, f), **kw) for f in files], ignore_index=True)
 
 
 def _sample(fr, fraction, seed):
@@ -211,7 +216,7 @@ def statistics(spark, idf_target, idf_source, list_of_cols="all", drop_cols=None
         else:
             tdic, th = tgt.column(c).dictionary, tgt_cat[c]
             if use_p:
-                f = _load_frequency(model_path, c)
+                f = _load_frequency(model_path, c, string_keys=True)
                 sk = {}
                 s_null = False
                 for k, v in zip(f[c].tolist(), f["p"].tolist()):

@@ -35,11 +35,12 @@ class KernelTimer:
         import torch
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1 in self.spans:
-            t = out.setdefault(name, [0.0, 0])
+        for name, e0, e1, nbytes in self.spans:
+            t = out.setdefault(name, [0.0, 0, 0])
             t[0] += e0.elapsed_time(e1)
             t[1] += 1
-        return {k: {"ms": v[0], "calls": v[1]} for k, v in out.items()}
+            t[2] += nbytes
+        return {k: {"ms": v[0], "calls": v[1], "input_bytes": v[2]} for k, v in out.items()}
 
 
 timer = None  # set to a KernelTimer() to collect per-call device times
@@ -54,7 +55,9 @@ def _host(t, nbytes=None):
     return a
 
 
-def _call(fn, name, *args):
+def _call(fn, name, *args, nbytes=0):
+    """nbytes: bytes of column data (+ validity bitmaps) one read of the call's input columns moves - the
+    algorithmic bytes of SURVEY.md 8(d), recorded with the device time so bench.py can quote GB/s per call."""
     if timer is None:
         _lib.check(fn(*args), name)
         return
@@ -63,8 +66,21 @@ def _call(fn, name, *args):
     e0.record()
     rc = fn(*args)
     e1.record()
-    timer.spans.append((name, e0, e1))
+    timer.spans.append((name, e0, e1, nbytes))
     _lib.check(rc, name)
+
+
+def input_bytes(frame, names) -> int:
+    """One read of `names`: n_rows * itemsize (+ n_rows / 8 where a validity bitmap exists)."""
+    if timer is None:
+        return 0
+    tot = 0
+    for n in names:
+        col = frame.column(n)
+        tot += frame.n_rows * (4 if col.anv_dtype in (_lib.ANV_F32, _lib.ANV_I32) else 8)
+        if col.has_validity:
+            tot += (frame.n_rows + 7) // 8
+    return tot
 
 
 def _stream():
@@ -99,7 +115,7 @@ def moments(frame: ColumnFrame, names):
     ws = _dev_bytes(ws_bytes)
     out = _dev_bytes(len(names) * _MOM_DT.itemsize)
     _call(L.anv_moments, "anv_moments", desc.data_ptr(), len(names), frame.n_rows, out.data_ptr(), ws.data_ptr(), ws_bytes,
-                             _stream())
+                             _stream(), nbytes=input_bytes(frame, names))
     launch_count += 2
     return _host(out).view(_MOM_DT).copy()
 
@@ -195,7 +211,7 @@ def histogram(frame: ColumnFrame, model: BinModel):
     specs, cuts = model.device()
     counts = _dev_bytes(n * stride * 8)
     _call(L.anv_hist, "anv_hist", desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, counts.data_ptr(),
-                          stride, _stream())
+                          stride, _stream(), nbytes=input_bytes(frame, model.names))
     launch_count += 1
     return _host(counts).view(np.uint64).reshape(n, stride).copy()
 
@@ -218,7 +234,8 @@ def moments_histogram(frame: ColumnFrame, model: BinModel):
     ws = _dev_bytes(ws_bytes)
     out = _dev_bytes(n * _MOM_DT.itemsize)
     _call(L.anv_moments_hist, "anv_moments_hist", desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, out.data_ptr(),
-                                  counts.data_ptr(), stride, ws.data_ptr(), ws_bytes, _stream())
+                                  counts.data_ptr(), stride, ws.data_ptr(), ws_bytes, _stream(),
+          nbytes=input_bytes(frame, model.names))
     launch_count += 2
     return (_host(out).view(_MOM_DT).copy(),
             _host(counts).view(np.uint64).reshape(n, stride).copy())
@@ -239,7 +256,7 @@ def bin_assign(frame: ColumnFrame, model: BinModel):
     desc, keep = frame.descriptors(model.names)
     specs, cuts = model.device()
     _call(L.anv_bin_assign, "anv_bin_assign", desc.data_ptr(), specs.data_ptr(), cuts.data_ptr(), n, frame.n_rows, model.max_bins,
-                                out.data_ptr(), out.stride(0), _stream())
+                                out.data_ptr(), out.stride(0), _stream(), nbytes=input_bytes(frame, model.names))
     launch_count += 1
     return out[:, :frame.n_rows]
 
@@ -266,7 +283,7 @@ def code_counts(frame: ColumnFrame, names):
         dcards = _to_dev(cards)
         counts = _dev_bytes(len(grp) * stride * 8)
         _call(L.anv_hist_codes, "anv_hist_codes", desc.data_ptr(), dcards.data_ptr(), len(grp), frame.n_rows, counts.data_ptr(),
-                                    stride, _stream())
+                                    stride, _stream(), nbytes=input_bytes(frame, grp))
         launch_count += 1
         h = _host(counts).view(np.uint64).reshape(len(grp), stride)
         for i, g in enumerate(grp):
@@ -348,7 +365,7 @@ def select_ranks(frame: ColumnFrame, names, ranks):
             drk = _to_dev(rk)
             dout = _dev_bytes(rk.size * 8)
             _call(L.anv_select_ranks, "anv_select_ranks", desc.data_ptr(), len(grp), frame.n_rows, drk.data_ptr(), rk.shape[1], kb,
-                                          dout.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+                                          dout.data_ptr(), ws.data_ptr(), ws_bytes, _stream(), nbytes=input_bytes(frame, grp))
             launch_count += 2 * (3 if kb == 32 else 7)
             out[np.asarray(idx)[:, None], np.arange(r0, r0 + rk.shape[1])[None, :]] = \
                 _host(dout).view(np.float64)[:rk.size].reshape(rk.shape)
@@ -399,7 +416,8 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
             drv = _dev_bytes(n * n_ranks * 8) if n_ranks else None
             _call(L.anv_mode_distinct, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv.data_ptr(), mr.data_ptr(),
                   nd.data_ptr(), drk.data_ptr() if drk is not None else None, n_ranks,
-                  drv.data_ptr() if drv is not None else None, ws.data_ptr(), ws_bytes, _stream())
+                  drv.data_ptr() if drv is not None else None, ws.data_ptr(), ws_bytes, _stream(),
+                  nbytes=input_bytes(frame, sub))
             launch_count += 3 + 3 * (kb // 8)
             hv = _host(mv).view(np.float64)[:n]
             hr = _host(mr).view(np.int64)[:n]
@@ -467,7 +485,7 @@ def hll_registers(frame: ColumnFrame, names, p: int):
     m = 1 << p
     desc, keep = frame.descriptors(names)
     regs = _dev_bytes(len(names) * m * 4)
-    _call(L.anv_hll_registers, "anv_hll_registers", desc.data_ptr(), len(names), frame.n_rows, p, regs.data_ptr(), _stream())
+    _call(L.anv_hll_registers, "anv_hll_registers", desc.data_ptr(), len(names), frame.n_rows, p, regs.data_ptr(), _stream(), nbytes=input_bytes(frame, names))
     launch_count += 1
     return _host(regs).view(np.uint32)[:len(names) * m].reshape(len(names), m).copy()
 

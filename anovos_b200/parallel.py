@@ -83,3 +83,42 @@ def gather_summaries(matrix: np.ndarray, device=None):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return [o[:int(c.item())].cpu().numpy() for o, c in zip(out, counts)]
+
+
+def bind_numa(device_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs: /sys/bus/pci/devices/<bdf>/numa_node), so
+    that pinned host buffers allocated afterwards are local to the GPU's PCIe root: torchrun does not bind its workers, and
+    a rank that lands on the other socket uploads at a fraction of the PCIe rate.  Call BEFORE the first pinned allocation.
+    -> dict describing what was done (bench.py reports it)."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if vis:
+            ent = vis.split(",")[device_index].strip()
+            h = pynvml.nvmlDeviceGetHandleByUUID(ent) if ent.startswith(("GPU-", "MIG-")) else pynvml.nvmlDeviceGetHandleByIndex(int(ent))
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        info.update(pci=bdf, node=node)
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus))
+    except Exception as ex:   # best effort: an unbound process still works, only slower over PCIe
+        info["error"] = repr(ex)
+    return info

@@ -55,6 +55,13 @@ def column_params(c: int, seed: int, shifted: bool = False):
 _DICTS = {}  # cardinality -> dictionary strings (shared by every chunk: built once)
 
 
+def numeric_ordinal(c: int, cat_every: int) -> int:
+    """Index of numeric column c among the NUMERIC columns of a mixed frame (every cat_every-th column is
+    categorical): family and null rate cycle over the numeric columns, so a mixed frame (75 % numeric /
+    25 % categorical) still holds all four families and null rates.  The Philox key stays the global column id."""
+    return c - c // cat_every if cat_every else c
+
+
 def _column_generator(rows: int, c: int, seed: int, shifted: bool, cat_every: int, row0: int):
     """-> (spark dtype, dictionary | None, has_nulls, loader) of global column id c; loader() launches the
     Philox kernel on the current stream and returns (values, validity words | None) on the device."""
@@ -75,7 +82,7 @@ def _column_generator(rows: int, c: int, seed: int, shifted: bool, cat_every: in
         if card not in _DICTS:
             _DICTS[card] = ["cat_%05d" % k for k in range(card)]
         return "string", _DICTS[card], rate > 0, load_codes
-    fam, a, b, rate = column_params(c, 42, shifted)
+    fam, a, b, rate = column_params(numeric_ordinal(c, cat_every), 42, shifted)
 
     def load_f32():
         torch = _lib.require_cuda()
@@ -276,10 +283,10 @@ def _twin(rows, row0, chunk, **kw):
     return (np.concatenate(vs) if len(vs) > 1 else vs[0]), (None if ms[0] is None else (np.concatenate(ms) if len(ms) > 1 else ms[0]))
 
 
-def host_column(rows: int, c: int, seed: int = 42, shifted: bool = False, row0: int = 0):
-    """Bit-identical NumPy twin of numeric column c of device_frame(rows, ..., seed, shifted) ->
+def host_column(rows: int, c: int, seed: int = 42, shifted: bool = False, row0: int = 0, cat_every: int = 0):
+    """Bit-identical NumPy twin of numeric column c of device_frame(rows, ..., seed, shifted, cat_every) ->
     (float32 values, bool valid).  row0 (multiple of 4): the rows [row0, row0 + rows) of a larger frame."""
-    fam, a, b, rate = column_params(c, 42, shifted)
+    fam, a, b, rate = column_params(numeric_ordinal(c, cat_every), 42, shifted)
     v, m = _twin(rows, row0, 1 << 22, seed=seed, column=c, kind=fam, a=a, b=b, null_rate=rate)
     return v, (np.ones(rows, bool) if m is None else m)
 
@@ -303,7 +310,7 @@ def host_table(rows: int, cols: int, seed: int = 42, first_col: int = 0, shifted
             codes, valid, dic = host_codes(rows, c, cat_every, seed)
             arr = pa.DictionaryArray.from_arrays(pa.array(codes, mask=None if valid.all() else ~valid), pa.array(dic)).cast(pa.string())
         else:
-            x, valid = host_column(rows, c, seed, shifted)
+            x, valid = host_column(rows, c, seed, shifted, cat_every=cat_every)
             arr = pa.array(x, mask=None if valid.all() else ~valid)
         arrays.append(arr)
         names.append("%s%04d" % (prefix, c))

@@ -86,6 +86,8 @@ typedef struct {
 
 /* ---- library ------------------------------------------------------------------- */
 int anv_version(void);
+/* sha1 of the sources the binary was built from (build-time define); "unknown" for an ad-hoc build. */
+const char* anv_source_hash(void);
 const char* anv_last_error(void);
 /* sm_count / cc_major / cc_minor / total_mem of the CURRENT device. */
 int anv_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);

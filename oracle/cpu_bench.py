@@ -80,3 +80,38 @@ def time_stats_generator(table, workers=None, target=None):
             pool.map(_drift_group, groups)
             t_drift = time.perf_counter() - t0
     return t_stats, t_drift, len(groups)
+
+
+# ---- parity leg of bench.py: the oracle's answers for a few columns of the bench frame at full length ---------------
+
+_MAKE = None   # (column id, seed, shifted) -> one-column pyarrow Table; set by oracle_columns before the fork
+
+
+def _oracle_column(job):
+    c, with_drift = job
+    import tempfile
+    from . import api as O
+    t = _MAKE(c, 42, False)
+    name = t.column_names[0]
+    out = {}
+    for fn in ("measures_of_counts", "measures_of_centralTendency", "measures_of_cardinality", "measures_of_dispersion",
+               "measures_of_percentiles", "measures_of_shape"):
+        df = getattr(O, fn)(t)
+        rec = df[df["attribute"] == name]
+        out[fn] = None if len(rec) == 0 else {k: v for k, v in rec.iloc[0].to_dict().items() if k != "attribute"}
+    if with_drift:
+        tt = _MAKE(c, 43, True)
+        with tempfile.TemporaryDirectory() as d:
+            r = O.statistics(tt, t, method_type="all", use_sampling=False, source_path=d)
+        out["drift"] = {m: float(r[m].iloc[0]) for m in ("PSI", "HD", "JSD", "KS")}
+    return name, out
+
+
+def oracle_columns(make_table, column_ids, drift_ids=()):
+    """dict column name -> {function name -> {field -> value}, "drift" -> metrics}: the oracle on the tables
+    `make_table(column id, seed, shifted)` builds (bench.py: the NumPy twin of the device generator), one process per column."""
+    global _MAKE
+    _MAKE = make_table
+    jobs = [(c, c in set(drift_ids)) for c in column_ids]
+    with mp.get_context("fork").Pool(max(1, len(jobs))) as pool:
+        return dict(pool.map(_oracle_column, jobs))

@@ -45,6 +45,11 @@ def test_device_generator_equals_numpy_twin(rows, row0):
             else:
                 assert np.array_equal(v.cpu().numpy(), _bits(valid)), (name, seed)
     cat = synth.device_frame(rows, 16, seed=42, cat_every=4, row0=row0)
+    for c in (4, 5, 6, 12):   # numeric columns of a mixed frame: family / null rate cycle over the numeric ordinal
+        d, v = cat.column(cat.columns[c]).device()
+        x, valid = synth.host_column(rows, c, 42, row0=row0, cat_every=4)
+        assert np.array_equal(d.cpu().numpy().view(np.uint32), x.view(np.uint32)), c
+        assert (v is None and valid.all()) or np.array_equal(v.cpu().numpy(), _bits(valid)), c
     for c in (3, 7, 11, 15):
         name = cat.columns[c]
         d, v = cat.column(name).device()

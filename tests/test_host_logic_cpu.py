@@ -65,3 +65,37 @@ def test_frames_to_matrix_mixed_dtypes():
     m, names = parallel.frames_to_matrix([f1, f2])
     assert names == ["mean", "mode_rows", "count", "nullable"]
     assert np.array_equal(m, np.array([[1.5, 3, 4, 1], [np.nan, np.nan, 5, np.nan]]), equal_nan=True)
+
+
+def test_drift_argument_normalisers_contract():
+    """validations.py:8-94 as behaviour: keyword-only reading, "all" = num + cat of the target, '|' strings, drops,
+    first-seen de-duplication, error types (reference test_validations.py:13-20 checks the ValueErrors)."""
+    import pyarrow as pa
+    import pytest
+    from anovos_b200.drift_stability.validations import check_distance_method, check_list_of_columns
+    t = pa.table({"a": [1.0, 2.0], "b": ["x", "y"], "c": [1, 2], "d": pa.array([True, False])})
+
+    @check_distance_method
+    @check_list_of_columns
+    def f(spark, idf_target, idf_source, *, list_of_cols="all", drop_cols=None, method_type="PSI"):
+        return list_of_cols, drop_cols, method_type
+
+    assert f(None, t, t) == (["a", "c", "b"], [], ["PSI"])                       # bool column is neither num nor cat
+    assert f(None, t, t, list_of_cols="a| b |a", drop_cols="b") == (["a"], [], ["PSI"])
+    assert f(None, idf_target=t, idf_source=t, list_of_cols=["c", "a", "c"], method_type="all") == (["c", "a"], [], ["PSI", "JSD", "HD", "KS"])
+    assert f(None, t, t, method_type="KS|HD")[2] == ["KS", "HD"]
+    with pytest.raises(ValueError):
+        f(None, t, t, list_of_cols=["a"], drop_cols=["a"])
+    with pytest.raises(ValueError):
+        f(None, t, t, list_of_cols="zz")
+    with pytest.raises(TypeError):
+        f(None, t, t, list_of_cols=3)
+    with pytest.raises(TypeError):
+        f(None, t, t, drop_cols=3)
+    with pytest.raises(TypeError):
+        f(None, t, t, method_type="XYZ")
+
+    @check_list_of_columns(columns="cols", drop="drops")
+    def g(spark, idf_target, *, cols="all", drops=None):
+        return cols, drops
+    assert g(None, t, cols="b|c") == (["b", "c"], [])

@@ -243,3 +243,27 @@ def test_iv_ig_host_path(income_part0, income_spark, nb_assoc):
             ae.IV_calculation(None, t, label_col="nope")
         with pytest.raises(TypeError):
             ae.IV_calculation(None, t, event_label=7)
+
+
+def test_saved_frequency_round_trip_keeps_string_keys(tmp_path):
+    """pre_existing_source=True must join on the strings that were saved: categories spelled like pandas' NA markers
+    ("NA", "None", "null", "nan", "N/A") or like numbers ("007", "1.0") are ordinary categories for Spark's CSV reader."""
+    import anovos.drift_stability.drift_detector as dd
+    rng = np.random.default_rng(3)
+    n = 6000
+    cats = ["NA", "None", "null", "nan", "N/A", "007", "1.0", "plain", "a,b"]
+    def mk(p, seed):
+        r = np.random.default_rng(seed)
+        return pa.table({"s": pa.array(r.choice(cats, n, p=p), mask=r.random(n) < 0.05), "x": pa.array(r.normal(0, 1, n))})
+    p0 = np.array([3, 2, 2, 1, 1, 2, 2, 4, 1], float); p0 /= p0.sum()
+    p1 = np.array([1, 3, 1, 2, 1, 3, 1, 3, 2], float); p1 /= p1.sum()
+    src, tgt = mk(p0, 1), mk(p1, 2)
+    kw = dict(method_type="all", use_sampling=False)
+    with cpu_engine.installed():
+        direct = dd.statistics(None, tgt, src, source_path=str(tmp_path / "m"), **kw).toPandas()
+        again = dd.statistics(None, tgt, None, pre_existing_source=True, source_path=str(tmp_path / "m"), **kw).toPandas()
+    exp = O.statistics(tgt, src, source_path=str(tmp_path / "o"), **kw)
+    _close_cols(direct, exp, ["PSI", "HD", "JSD", "KS"])
+    _close_cols(again, direct, ["PSI", "HD", "JSD", "KS"])
+    f = pd.read_csv(tmp_path / "m" / "drift_statistics" / "frequency_counts" / "s" / "part-00000.csv", dtype=str, keep_default_na=False)
+    assert sorted(k for k in f["s"] if k != "") == sorted(cats)
