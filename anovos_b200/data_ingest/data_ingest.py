@@ -115,8 +115,22 @@ def read_dataset(spark, file_path, file_type, file_configs={}):
                     lo, hi = mm["min"].as_py(), mm["max"].as_py()
                     if lo is None or (-(1 << 31) <= lo and hi < (1 << 31)):
                         t = t.set_column(i, fld.name, t.column(i).cast(pa.int32()))
+    elif file_type == "json":
+        # Spark's json source reads JSON Lines; inferred struct fields come out sorted by name (JsonInferSchema),
+        # integers as bigint, fractions as double
+        import pyarrow.json as pajson
+        for f in _part_files(file_path, "json"):
+            per_file[f] = pajson.read_json(f)
+        t = pa.concat_tables(list(per_file.values()), promote_options="default")
+        t = t.select(sorted(t.column_names))
+        per_file = {f: tb.select([c for c in sorted(t.column_names) if c in tb.column_names]) for f, tb in per_file.items()}
+    elif file_type == "avro":
+        from .avro_io import read_avro
+        for f in _part_files(file_path, "avro"):
+            per_file[f] = read_avro(f)
+        t = pa.concat_tables(list(per_file.values()), promote_options="default")
     else:
-        raise NotImplementedError("file_type %r: only csv and parquet are part of the B200 hot-path build" % file_type)
+        raise NotImplementedError("file_type %r: csv, parquet, json and avro are supported" % file_type)
     if cores:
         return _as_spark_partitions(t, per_file, int(cores), file_type, file_type == "csv" and header)
     return ColumnFrame.from_arrow(t)
@@ -153,38 +167,60 @@ def _as_spark_partitions(t, per_file, cores, file_type, header):
 
 
 def write_dataset(idf, file_path, file_type, file_configs={}, column_order=[]):
-    """Writes a ResultFrame / pandas / pyarrow object as `<file_path>/part-00000.<ext>` (Spark-style directory).
-    mode: error (default) | overwrite."""
+    """Writes a ColumnFrame / PartitionedFrame (D2H of values + validity, dictionary decode), ResultFrame, pandas or
+    pyarrow object as `<file_path>/part-00000.<ext>` (Spark-style directory + _SUCCESS).  file_type: csv | parquet |
+    json | avro; file_configs: header, delimiter, compression (avro: uncompressed | deflate | snappy),
+    mode: error (default) | overwrite | append.  Reference data_ingest.py:54-110."""
+    import shutil
     import pandas as pd
     import pyarrow as pa
     import pyarrow.parquet as pq
     if isinstance(idf, ResultFrame):
-        df = idf.toPandas()
+        tb = pa.Table.from_pandas(idf.toPandas(), preserve_index=False)
     elif isinstance(idf, pd.DataFrame):
-        df = idf
+        tb = pa.Table.from_pandas(idf, preserve_index=False)
     elif isinstance(idf, pa.Table):
-        df = idf.to_pandas()
+        tb = idf
+    elif isinstance(idf, ColumnFrame) or getattr(idf, "is_partitioned", False):
+        tb = (idf.materialize() if getattr(idf, "is_partitioned", False) else idf).to_arrow()
     else:
-        raise TypeError("write_dataset: pass a ResultFrame, pandas DataFrame or pyarrow Table")
+        raise TypeError("write_dataset: pass a ColumnFrame, ResultFrame, pandas DataFrame or pyarrow Table")
     if column_order:
-        if len(column_order) != len(df.columns):
+        if len(column_order) != len(tb.column_names):
             raise ValueError("Count of column(s) specified in column_order argument do not match Dataframe")
-        diff = [c for c in column_order if c not in set(df.columns)]
+        diff = [c for c in column_order if c not in set(tb.column_names)]
         if diff:
             raise ValueError("Column(s) specified in column_order argument not found in Dataframe: " + str(diff))
-        df = df[list(column_order)]
+        tb = tb.select(list(column_order))
     mode = file_configs.get("mode", "error")
+    part = 0
     if os.path.exists(file_path):
         if mode == "error":
             raise FileExistsError(file_path)
-        for f in os.listdir(file_path):
-            os.remove(os.path.join(file_path, f))
+        if mode == "overwrite":
+            shutil.rmtree(file_path)          # part files AND Spark-style partition sub-directories
+        elif mode == "append":
+            part = sum(1 for f in os.listdir(file_path) if f.startswith("part-"))
+        else:
+            raise ValueError("mode must be error, overwrite or append")
     os.makedirs(file_path, exist_ok=True)
+    stem = os.path.join(file_path, "part-%05d" % part)
     if file_type == "csv":
-        df.to_csv(os.path.join(file_path, "part-00000.csv"), index=False, header=_truthy(file_configs.get("header", "false")),
-                  sep=file_configs.get("delimiter", ","))
+        import pyarrow.csv as pacsv           # Arrow keeps nullable integers integers (pandas would print 39.0)
+        pacsv.write_csv(tb, stem + ".csv", pacsv.WriteOptions(include_header=_truthy(file_configs.get("header", "false")),
+                                                              delimiter=file_configs.get("delimiter", ","), quoting_style="needed"))
     elif file_type == "parquet":
-        pq.write_table(pa.Table.from_pandas(df, preserve_index=False), os.path.join(file_path, "part-00000.parquet"))
+        pq.write_table(tb, stem + ".parquet")
+    elif file_type == "json":
+        import json
+        with open(stem + ".json", "w") as fh:      # JSON Lines; null fields are omitted, like Spark's writer
+            for row in tb.to_pylist():
+                fh.write(json.dumps({k: v for k, v in row.items() if v is not None}, ensure_ascii=False) + "\n")
+    elif file_type == "avro":
+        from .avro_io import write_avro
+        codec = {"uncompressed": "null", "none": "null"}.get(str(file_configs.get("compression", "snappy")).lower(),
+                                                             str(file_configs.get("compression", "snappy")).lower())
+        write_avro(tb, stem + ".avro", codec)
     else:
         raise NotImplementedError("file_type %r" % file_type)
     open(os.path.join(file_path, "_SUCCESS"), "w").close()

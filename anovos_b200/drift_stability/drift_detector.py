@@ -85,35 +85,6 @@ def _load_frequency(model_path, col, string_keys=False):
     return pd.concat([pd.read_csv(os.path.join(d, f), **kw) for f in files], ignore_index=True)
 
 
-def _sample(fr, fraction, seed):
-    """Bernoulli row sample (reference data_sampling.py:148 `idf.sample(False, fraction, seed)`).
-    Spark's XORShift sampler is not reproducible here: own seeded RNG, documented as
-    non-parity (SURVEY C#14).  Benchmarks and parity runs use use_sampling=False."""
-    import torch
-    from ..frame import Column, ColumnFrame
-    from collections import OrderedDict
-    g = torch.Generator(device="cuda")
-    g.manual_seed(int(seed))
-    keep = torch.rand(fr.n_rows, device="cuda", generator=g) < fraction
-    idx = torch.nonzero(keep).flatten()
-    n = int(idx.numel())
-    cols = OrderedDict()
-    for name in fr.columns:
-        c = fr.column(name)
-        if c.kind == "other":
-            cols[name] = Column(name, c.sdtype, n)
-            continue
-        d, v = c.device()
-        nd = d.index_select(0, idx)
-        nv = None
-        if v is not None:
-            bits = ((v[(idx >> 5)] >> (idx & 31).to(torch.int32)) & 1).to(torch.uint8).cpu().numpy().astype(bool)
-            from ..frame import _pack_validity
-            nv = torch.from_numpy(_pack_validity(bits)).cuda()
-        cols[name] = Column(name, c.sdtype, n, dev=nd, dev_valid=nv, anv_dtype=c.anv_dtype, dictionary=c.dictionary)
-    return ColumnFrame(cols, n)
-
-
 @check_distance_method
 @check_list_of_columns
 def statistics(spark, idf_target, idf_source, list_of_cols="all", drop_cols=None, method_type="PSI",
@@ -135,18 +106,13 @@ def statistics(spark, idf_target, idf_source, list_of_cols="all", drop_cols=None
     if other:
         raise TypeError("columns %s have a dtype the drift path does not handle" % other)
 
-    if use_sampling and (getattr(tgt, "is_partitioned", False) or getattr(src, "is_partitioned", False)):
-        if tgt.count() > sample_size or (src is not None and src.count() > sample_size):
-            raise NotImplementedError("use_sampling=True is not implemented for row-partitioned frames: pass "
-                                      "use_sampling=False (the whole frame is cheap to scan on the GPU)")
-        use_sampling = False
-    if use_sampling:
-        if sample_method != "random" and (tgt.count() > sample_size or (src is not None and src.count() > sample_size)):
-            raise NotImplementedError("only sample_method='random' is implemented on the B200 path")
+    if use_sampling:      # :187-211 - Spark's Bernoulli / sampleBy row set, reproduced on the device (data_sampling.py)
+        from ..data_ingest.data_sampling import data_sample
+        kw = dict(strata_cols=strata_cols, method_type=sample_method, stratified_type=stratified_type, seed_value=sample_seed)
         if tgt.count() > sample_size:
-            tgt = _sample(tgt, sample_size / tgt.count(), sample_seed)
+            tgt = data_sample(tgt, fraction=sample_size / tgt.count(), **kw)
         if src is not None and src.count() > sample_size:
-            src = _sample(src, sample_size / src.count(), sample_seed)
+            src = data_sample(src, fraction=sample_size / src.count(), **kw)
     count_target = tgt.count()
     count_source = src.count() if src is not None else None
 

@@ -288,6 +288,34 @@ class ColumnFrame:
     def __contains__(self, name):
         return name in self._cols
 
+    def to_arrow(self):
+        """-> pyarrow Table (D2H of values and validity; string columns decoded through their dictionary).  Columns of
+        "other" kind carry no data on this path and come back as all-null columns."""
+        import pyarrow as pa
+        arrays = []
+        for n, c in self._cols.items():
+            if c.kind == "other":
+                arrays.append(pa.nulls(self.n_rows))
+                continue
+            if c._host is not None and c._dev is None:
+                vals, words = np.asarray(c._host), c._host_valid
+            else:
+                d, v = c.device()
+                vals, words = d.cpu().numpy(), (None if v is None else v.cpu().numpy())
+            mask = None
+            if words is not None:
+                bits = np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:self.n_rows]
+                mask = bits == 0
+            if c.dictionary is not None:
+                idx = pa.array(vals[:self.n_rows], type=pa.int32(), mask=mask)
+                arrays.append(pa.DictionaryArray.from_arrays(idx, pa.array(c.dictionary, type=pa.string())).cast(pa.string()))
+            else:
+                arrays.append(pa.array(vals[:self.n_rows], mask=mask))
+        return pa.table(arrays, names=list(self._cols))
+
+    def to_pandas(self):
+        return self.to_arrow().to_pandas()
+
     # ---- constructors -----------------------------------------------------------------
     @staticmethod
     def from_arrow(table) -> "ColumnFrame":
@@ -385,7 +413,11 @@ class ColumnFrame:
         key = ("desc", tuple(names))
         hit = self._cache.get(key)
         if hit is not None:
-            return hit
+            # valid only while every column still holds the buffers the descriptors point at: a chunk released with
+            # drop_device() (and re-uploaded later) must not be kept alive - or addressed - through this cache
+            if all(self._cols[n]._dev is d and self._cols[n]._dev_valid is v for n, (d, v) in zip(names, hit[1])):
+                return hit
+            del self._cache[key]
         arr = (_lib.AnvColumn * max(len(names), 1))()
         keep = []
         for i, nme in enumerate(names):

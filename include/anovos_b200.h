@@ -189,6 +189,18 @@ int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, int 
                       double* mode_value, int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks,
                       int n_ranks, double* rank_values, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Spark's Bernoulli row sampler (the DEFAULT path of drift_detector.statistics: use_sampling=True ->
+ *      data_sampling.py:122-149 `idf.sample(False, fraction, seed)` / `stat.sampleBy("merge", fractions, seed)`,
+ *      drift_detector.py:187-211).  One partition per call: Spark seeds XORShiftRandom with seed + partitionIndex,
+ *      draws one nextDouble() per row and keeps the row when x < fraction[stratum].  thresholds [dev] n_strata
+ *      uint64 = ceil(fraction * 2^53) (x is a 53-bit integer * 2^-53, so the comparison is exact in integers);
+ *      strata [dev] int32 stratum id per row or NULL (every row uses thresholds[0]; ids outside [0, n_strata) are
+ *      never kept); keep [dev] ceil(n_rows/32) bitmap words, LSB first.  The stream is generated in parallel by
+ *      jumping the GF(2)-linear recurrence ahead (sample.cu). */
+uint64_t anv_spark_hash_seed(int64_t seed); /* XORShiftRandom.hashSeed: the generator state after setSeed(seed) */
+int anv_spark_sample_mask(int64_t n_rows, int64_t seed, const int32_t* strata, const uint64_t* thresholds,
+                          int n_strata, uint32_t* keep, void* stream);
+
 /* ---- synthetic column generator used by bench.py / tests: Philox4x32-10
  *      keyed by (seed, column), counter = row.  family: 0 normal(a,b) 1 lognormal(0,b)
  *      2 uniform(a,b) 3 zero-inflated exponential(scale b, 70% zeros).

@@ -597,19 +597,111 @@ def _group_counts(table, col, is_binned_numeric):
     return groups, (has_null and not is_binned_numeric)
 
 
+def _partition_slices(table):
+    md = table.schema.metadata or {}
+    rows = json.loads(md[b"spark_partition_rows"]) if b"spark_partition_rows" in md else [table.num_rows]
+    out, r0 = [], 0
+    for k in rows:
+        out.append((r0, k))
+        r0 += k
+    return out
+
+
+def _cast_string(v, sdtype):
+    if sdtype == "string":
+        return str(v)
+    if sdtype in ("int", "bigint", "long"):
+        return str(int(v))
+    if sdtype == "float":
+        return S.java_double_to_string(float(str(np.float32(v))))
+    return S.java_double_to_string(float(v))
+
+
+def data_sample(table, strata_cols="all", drop_cols=[], fraction=0.1, method_type="random", stratified_type="population",
+                seed_value=12, unique_threshold=0.5):
+    """data_sampling.py:8-149 on a pyarrow Table (Spark partitions from the `spark_partition_rows` metadata, else one
+    partition): Bernoulli sampling with Spark's XORShiftRandom(seed + partition index), one draw per row
+    (`sample`) or per row surviving na.drop (`sampleBy`)."""
+    if type(fraction) != float and type(fraction) != int:
+        raise TypeError("Invalid input for fraction")
+    if fraction <= 0 or fraction > 1:
+        raise TypeError("Invalid input for fraction: fraction value is between 0 and 1")
+    if type(seed_value) != int:
+        raise TypeError("Invalid input for seed_value")
+    if method_type not in ["stratified", "random"]:
+        raise TypeError("Invalid input for data_sample method_type")
+    parts = _partition_slices(table)
+    if method_type == "random":
+        keep = np.concatenate([S.bernoulli_keep(k, seed_value + i, fraction) for i, (r0, k) in enumerate(parts)]) \
+            if table.num_rows else np.zeros(0, bool)
+        return table.filter(pa.array(keep))
+    if type(unique_threshold) != float and type(unique_threshold) != int:
+        raise TypeError("Invalid input for unique_threshold")
+    if unique_threshold > 1 and type(unique_threshold) != int:
+        raise TypeError("Invalid input for unique_threshold: unique_threshold can only be integer if larger than 1")
+    if unique_threshold <= 0:
+        raise TypeError("Invalid input for unique_threshold: unique_threshold value is either between 0 and 1, or an integer > 1")
+    if stratified_type not in ["population", "balanced"]:
+        raise TypeError("Invalid input for stratified_type")
+    if isinstance(strata_cols, str) and strata_cols == "all":
+        strata_cols = table.column_names
+    strata_cols = _split(strata_cols)
+    drop_cols = _split(drop_cols)
+    strata_cols = list(dict.fromkeys(e for e in strata_cols if e not in drop_cols))
+    if not strata_cols:
+        raise TypeError("Missing strata_cols value")
+    N = table.num_rows
+    skip = []
+    for c in strata_cols:
+        if c not in table.column_names:
+            raise TypeError("Invalid input for strata_cols: " + c + " does not exist")
+        p = _profiles(table, [c])[c]
+        distinct = p.distinct() + (1 if p.n < N else 0)          # distinct() keeps the null group
+        if float(distinct) > (unique_threshold * float(N) if unique_threshold <= 1 else unique_threshold):
+            skip.append(c)
+    if skip:
+        warnings.warn("Columns dropped from strata due to high cardinality: " + ",".join(skip))
+    strata_cols = [c for c in strata_cols if c not in skip]
+    if not strata_cols:
+        warnings.warn("No Stratified Sampling Computation - No strata column(s) to sample")
+        return table
+    profs = _profiles(table, strata_cols)
+    ok = np.ones(N, bool)
+    for c in strata_cols:
+        ok &= profs[c].valid
+    merge = np.array(["".join(_cast_string(profs[c].values[i], profs[c].sdtype) for c in strata_cols) if ok[i] else ""
+                      for i in range(N)], dtype=object)
+    keys, counts = np.unique(merge[ok].astype(str), return_counts=True) if ok.any() else (np.array([]), np.array([]))
+    frac = {k: float(fraction) for k in keys}
+    if stratified_type == "balanced" and len(keys):
+        smallest = int(counts.min())
+        frac = {k: float(fraction * smallest / int(c)) for k, c in zip(keys.tolist(), counts.tolist())}
+    keep = np.zeros(N, bool)
+    for i, (r0, k) in enumerate(parts):
+        idx = np.flatnonzero(ok[r0:r0 + k]) + r0                 # the rows that reach the rand() filter, in order
+        if idx.size:
+            f = np.array([frac[str(m)] for m in merge[idx]])
+            keep[idx] = S.bernoulli_keep(idx.size, seed_value + i, f)
+    return table.filter(pa.array(keep))
+
+
 def statistics(idf_target, idf_source, *, list_of_cols="all", drop_cols=None, method_type="PSI",
                bin_method="equal_range", bin_size=10, threshold=0.1, use_sampling=True, sample_size=100000,
                pre_existing_source=False, source_save=True, source_path="NA",
-               model_directory="drift_statistics", return_groups=False):
-    """drift_detector.py:16-371.  Sampling (:187-211) is not restated: callers must
-    keep both frames <= sample_size or pass use_sampling=False (Spark Bernoulli
-    sampling is RNG-dependent: parity unpinned)."""
+               model_directory="drift_statistics", return_groups=False, sample_method="random", strata_cols="all",
+               stratified_type="population", sample_seed=42):
+    """drift_detector.py:16-371, including the default sampling step (:187-211 -> data_sample)."""
     cols = _check_columns(idf_target, list_of_cols, drop_cols)
     methods = _check_methods(method_type)
     num_cols = S.segregate(idf_target.select(cols))[0]
+    if use_sampling:
+        if idf_target.num_rows > sample_size:
+            idf_target = data_sample(idf_target, strata_cols=strata_cols, fraction=sample_size / idf_target.num_rows,
+                                     method_type=sample_method, stratified_type=stratified_type, seed_value=sample_seed)
+        if idf_source is not None and idf_source.num_rows > sample_size:
+            idf_source = data_sample(idf_source, strata_cols=strata_cols, fraction=sample_size / idf_source.num_rows,
+                                     method_type=sample_method, stratified_type=stratified_type, seed_value=sample_seed)
     n_t, n_s = idf_target.num_rows, (idf_source.num_rows if idf_source is not None else None)
-    if use_sampling and (n_t > sample_size or (n_s or 0) > sample_size):
-        raise NotImplementedError("oracle: Bernoulli sampling is not restated (parity unpinned)")
     if source_path == "NA":
         source_path = "intermediate_data"
     model_path = source_path + "/" + model_directory

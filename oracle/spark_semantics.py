@@ -682,3 +682,66 @@ def approx_count_distinct(values: np.ndarray, sdtype: str, rsd=None):
     p = hll_precision(rsd)
     regs = hll_registers(hll_hashes(values, sdtype), p)
     return hll_estimate(regs, p)
+
+
+# ----------------------------------------------------------------------------
+# Spark's row samplers (data_sampling.py:122-149 -> Dataset.sample / stat.sampleBy).  Un-vendored classes
+# org.apache.spark.util.random.{XORShiftRandom, BernoulliCellSampler} and catalyst Rand (Spark 3.x), restated from
+# their published algorithm.  PARITY UNPINNED for the kept row set: the reference holds no vector (its test checks
+# count ranges on data/data_sample/test_data_sample.csv only, tests/test_data_sampling_cpu.py).
+# ----------------------------------------------------------------------------
+
+_M32 = 0xFFFFFFFF
+_M64 = 0xFFFFFFFFFFFFFFFF
+
+
+def _murmur3_bytes(data: bytes, seed: int) -> int:
+    """scala.util.hashing.MurmurHash3.bytesHash (len % 4 == 0 is all XORShiftRandom needs)."""
+    h = seed & _M32
+    for i in range(0, len(data) - len(data) % 4, 4):
+        k = int.from_bytes(data[i:i + 4], "little")
+        k = (k * 0xcc9e2d51) & _M32
+        k = ((k << 15) | (k >> 17)) & _M32
+        k = (k * 0x1b873593) & _M32
+        h ^= k
+        h = ((h << 13) | (h >> 19)) & _M32
+        h = (h * 5 + 0xe6546b64) & _M32
+    h ^= len(data)
+    h ^= h >> 16
+    h = (h * 0x85ebca6b) & _M32
+    h ^= h >> 13
+    h = (h * 0xc2b2ae35) & _M32
+    h ^= h >> 16
+    return h
+
+
+def xorshift_hash_seed(seed: int) -> int:
+    """XORShiftRandom.hashSeed: MurmurHash3 of the 8 big-endian bytes of the (Java long) seed, twice."""
+    b = (seed & _M64).to_bytes(8, "big")
+    low = _murmur3_bytes(b, 0x3c074a61)
+    high = _murmur3_bytes(b, low)
+    return ((high << 32) | low) & _M64
+
+
+def xorshift_uniform53(seed: int, n: int) -> np.ndarray:
+    """The first n nextDouble() draws of XORShiftRandom(seed) as 53-bit integers k (the double is k * 2^-53)."""
+    s = xorshift_hash_seed(seed)
+    out = np.empty(n, dtype=np.uint64)
+
+    def nxt(s):
+        s ^= (s << 21) & _M64
+        s ^= s >> 35
+        s ^= (s << 4) & _M64
+        return s
+    for i in range(n):
+        s = nxt(s)
+        hi = s & ((1 << 26) - 1)
+        s = nxt(s)
+        out[i] = (hi << 27) + (s & ((1 << 27) - 1))
+    return out
+
+
+def bernoulli_keep(n: int, seed: int, fractions) -> np.ndarray:
+    """bool[n]: row i of ONE partition is kept when draw_i < fractions[i] (scalar fraction or per-row array)."""
+    x = xorshift_uniform53(seed, n).astype(np.float64) * 2.0 ** -53     # exact: k < 2^53
+    return x < np.asarray(fractions, dtype=np.float64)

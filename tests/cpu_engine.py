@@ -209,13 +209,30 @@ def _host_device(self):
     return self._dev, self._dev_valid
 
 
+def sample_mask(n_rows, seed, thresholds, strata=None):
+    """Stand-in of data_sampling.sample_mask (csrc/sample.cu): the oracle's sequential XORShiftRandom stream."""
+    import torch
+    x = S.xorshift_uniform53(seed, n_rows)
+    thr = np.asarray(thresholds, dtype=np.uint64)
+    if strata is None:
+        keep = x < thr[0]
+    else:
+        g = strata.numpy().astype(np.int64)
+        ok = (g >= 0) & (g < len(thr))
+        keep = ok & (x < thr[np.where(ok, g, 0)])
+    return torch.from_numpy(keep)
+
+
 @contextlib.contextmanager
 def installed():
     names = ["moments", "histogram", "moments_histogram", "code_counts", "drift_reduce", "select_ranks", "sort_mode_distinct",
              "hll_registers", "bin_assign"]
     saved = {n: getattr(engine, n) for n in names}
     saved_req, saved_up, saved_dev = _lib.require_cuda, framemod.Column.upload_async, framemod.Column.device
+    from anovos_b200.data_ingest import data_sampling
+    saved_mask = data_sampling.sample_mask
     try:
+        data_sampling.sample_mask = sample_mask
         for n in names:
             setattr(engine, n, globals()[n])
         proxy = _TorchProxy()
@@ -227,3 +244,4 @@ def installed():
         for n, f in saved.items():
             setattr(engine, n, f)
         _lib.require_cuda, framemod.Column.upload_async, framemod.Column.device = saved_req, saved_up, saved_dev
+        data_sampling.sample_mask = saved_mask

@@ -27,8 +27,10 @@ def test_read_csv_and_parquet_typing(tmp_path, income):
     pq.write_table(small, str(p / "part-00000.snappy.parquet"))
     fp = read_dataset(None, str(p), "parquet")
     assert fp.columns == small.column_names and dict(fp.dtypes)["fnlwgt"] == "int"
+    with pytest.raises(FileNotFoundError):
+        read_dataset(None, str(p), "avro")            # a directory without .avro part files
     with pytest.raises(NotImplementedError):
-        read_dataset(None, str(p), "avro")
+        read_dataset(None, str(p), "orc")
     # writer: Spark-style directory with a part file and _SUCCESS, mode error / overwrite
     import pandas as pd
     out = tmp_path / "out"
@@ -92,3 +94,55 @@ def test_flatten_and_transpose_dataframe():
     tr = transpose_dataframe(df, "summary").toPandas()
     assert tr.columns.tolist() == ["key", "count", "max", "mean"]
     assert tr.values.tolist() == [["age", 4.0, 55.0, 42.75], ["income", 3.0, 9000.0, 7333.3]]
+
+
+def test_json_avro_round_trip_and_frame_writer(tmp_path, income):
+    """file types "json" and "avro" of read_dataset / write_dataset (reference data_ingest.py:23-110), ColumnFrame ->
+    file (ADVICE: frames returned by attribute_binning / outlier treatment must be writable), overwrite of a directory
+    that holds sub-directories, append."""
+    import numpy as np
+    from anovos.data_ingest.data_ingest import read_dataset, write_dataset
+    from anovos_b200.frame import ColumnFrame
+    small = income.slice(0, 300).select(["age", "workclass", "logfnl", "fnlwgt", "income"])
+    for ftype, cfg in (("json", {}), ("avro", {}), ("avro", {"compression": "deflate"}), ("avro", {"compression": "uncompressed"}),
+                       ("parquet", {}), ("csv", {"header": "True"})):
+        out = tmp_path / (ftype + "_" + cfg.get("compression", "x"))
+        write_dataset(small, str(out), ftype, dict(cfg, mode="overwrite"))
+        fr = read_dataset(None, str(out), ftype, {"header": "True", "inferSchema": "True"})
+        assert fr.count() == 300 and sorted(fr.columns) == sorted(small.column_names)
+        if ftype == "json":
+            assert fr.columns == sorted(small.column_names)          # Spark's JSON inference sorts the fields by name
+            assert dict(fr.dtypes)["age"] == "bigint"                # ... and reads integers as LongType
+        else:
+            assert dict(fr.dtypes)["age"] == "int"
+        back = fr.to_arrow()
+        for c in small.column_names:
+            a, b = back.column(c).to_pylist(), small.column(c).to_pylist()
+            assert all((x is None and y is None) or x == y or (isinstance(y, float) and abs(x - y) <= 1e-12 * abs(y))
+                       for x, y in zip(a, b)), (ftype, c)
+    # a ColumnFrame goes out the same way (no device needed for a host-resident frame)
+    fr = ColumnFrame.from_arrow(small)
+    d = tmp_path / "frame_out"
+    os.makedirs(d / "nested=1")
+    open(d / "nested=1" / "part-00000.csv", "w").close()
+    write_dataset(fr, str(d), "parquet", {"mode": "overwrite"})       # rmtree: sub-directories do not break overwrite
+    assert sorted(os.listdir(d)) == ["_SUCCESS", "part-00000.parquet"]
+    write_dataset(fr, str(d), "parquet", {"mode": "append"})
+    assert read_dataset(None, str(d), "parquet").count() == 600
+    assert pq.read_table(str(d / "part-00000.parquet")).equals(small)
+
+
+def test_save_stats_layout(tmp_path):
+    """report_preprocessing.save_stats (:40-128): <master_path>/<function_name>.csv, header, no index; reread."""
+    import pandas as pd
+    from anovos.data_report.report_preprocessing import save_stats
+    from anovos_b200.result import ResultFrame
+    df = pd.DataFrame({"attribute": ["age", "fnlwgt"], "mean": [38.5816, 189778.3665], "mode": ["36", None]})
+    save_stats(None, ResultFrame(df), str(tmp_path / "stats"), "measures_of_centralTendency")
+    f = tmp_path / "stats" / "measures_of_centralTendency.csv"
+    assert f.read_text().splitlines()[0] == "attribute,mean,mode"
+    assert pd.read_csv(f).equals(pd.read_csv(f)) and len(pd.read_csv(f)) == 2
+    back = save_stats(None, df, str(tmp_path / "stats"), "again", reread=True)
+    assert back.columns == ["attribute", "mean", "mode"] and back.count() == 2
+    with pytest.raises(NotImplementedError):
+        save_stats(None, df, str(tmp_path), "x", run_type="emr")
