@@ -679,6 +679,492 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   return ANV_OK;
 }
 
+
+// =====================================================================================================================
+// Partition + count path for 32-bit keys (F32 / I32 columns): what mode / distinct / percentiles need is the multiset of
+// keys in key ORDER, not a sorted array - so the columns are not sorted at all:
+//   sample     32 * P keys per column (stratified row positions), sorted with the LSD kernels above (tiny);
+//   split      P - 1 splitters = every 32nd sample key, plus the key of zero as a forced splitter, and a 4096-cell
+//              lookup table over the top 12 key bits that narrows the splitter search to a few steps;
+//   partition  ONE read of the raw column: every key finds its bucket (lower_bound over the splitters).  A key EQUAL to a
+//              splitter is only counted (warp-aggregated atomics) - any value frequent enough to unbalance a bucket is a
+//              splitter with overwhelming probability (it occupies >= 32 sample slots), so heavy hitters, exact zeros and
+//              discrete-valued columns never reach the key buffer; the other keys are appended to their bucket's slab
+//              (capacity 4x the mean bucket; the open 32-byte sectors of all buckets stay in L2 until they are full);
+//   cum        prefix sums over the interleaved (bucket, splitter) counts: total order of the column => every requested
+//              rank resolves to a splitter value directly or to (bucket, local rank);
+//   count      one CTA per bucket: shared-memory hash table key -> multiplicity (buckets larger than the table are swept
+//              several times, each sweep taking one hash class), distinct count and longest run per bucket, in-bucket radix
+//              select for the few buckets that hold a requested rank.
+// HBM traffic: one read of the column + ~1 write and 1 read of the keys that are not splitters (vs ~14 words per key for
+// the LSD path); no ranking, no stable scatter.  Counting is integer everywhere => deterministic results (the slab order is
+// not, and does not matter).  A bucket that overflows its slab or a hash table that fills up raises a per-column flag; the
+// host then redoes that column on the LSD path.
+constexpr uint32_t PC_ZERO_KEY = 0x80000000u;    // key of +-0.0 / integer 0: always a splitter, doubles as EMPTY in the hash table
+constexpr int PC_OVERSAMPLE = 32;
+constexpr int PC_LUT_BITS = 12;
+constexpr int PC_LUT_CELLS = 1 << PC_LUT_BITS;
+constexpr int PC_SLOTS_LOG = 13;
+constexpr int PC_SLOTS = 1 << PC_SLOTS_LOG;      // hash table slots per CTA (64 KB: keys + counts)
+constexpr int PC_SWEEP_KEYS = 3072;              // keys one sweep of the table is sized for
+constexpr int PC_TILES_PER_CTA = 32;             // partition kernel: 32 x 4096 rows per CTA (amortises the splitter load)
+constexpr int PC_MAX_RANKS = 16;
+
+struct PcCol {                     // per column, in the workspace (zeroed per call)
+  unsigned long long n_valid;      // non-null values
+  unsigned long long distinct;     // sum of the buckets' distinct counts + splitters that occur
+  unsigned long long best;         // max over (multiplicity << 32 | ~key): the mode, ties -> smallest key
+  int overflow;
+  int n_queries;                   // ranks that fall inside a bucket
+  int q_bucket[PC_MAX_RANKS];
+  uint32_t q_local[PC_MAX_RANKS];  // 1-based rank inside the bucket
+  int q_slot[PC_MAX_RANKS];        // index into rank_values
+};
+
+struct PcParams {
+  const anv_column_t* cols;
+  int n_cols;
+  int64_t n_rows;
+  int P, NS, NB;                   // NS = P splitters (P - 1 from the sample + zero), NB = NS + 1 buckets
+  uint32_t cap;                    // slab capacity per bucket (keys)
+  int64_t m;                       // sample slots per column
+  uint32_t* split;                 // [n_cols][NS]
+  uint16_t* lut;                   // [n_cols][PC_LUT_CELLS + 1]
+  uint32_t* cursor;                // [n_cols][NB]  keys appended to each bucket
+  uint32_t* cnt_eq;                // [n_cols][NS]  keys equal to each splitter
+  uint32_t* cum;                   // [n_cols][2 * NB]  inclusive prefix over lt_0, eq_0, lt_1, eq_1, ...
+  uint32_t* slab;                  // [n_cols][NB][cap]
+  PcCol* st;
+};
+
+template <typename T> __device__ __forceinline__ T load_elem(const void* base, int64_t row) {
+  return reinterpret_cast<const T*>(base)[row];
+}
+
+// ---- sample: m stratified row positions per column -> keys (nulls and zeros dropped), compacted into the LSD buffers ----
+__global__ void __launch_bounds__(ANV_BLOCK) pc_sample_kernel(const SortParams<uint32_t> S, const int64_t n_rows, const int64_t m) {
+  const int c = blockIdx.y;
+  const anv_column_t col = S.cols[c];
+  const int64_t i = (int64_t)blockIdx.x * ANV_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool ok = false;
+  uint32_t key = 0;
+  if (i < m) {
+    const int64_t stride = n_rows / m > 0 ? n_rows / m : 1;
+    uint32_t h = (uint32_t)i * 0x9E3779B1u + (uint32_t)c * 0x85EBCA6Bu;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    const int64_t row = i * stride + (int64_t)(h % (uint32_t)stride);
+    if (row < n_rows) {
+      ok = col.validity ? ((col.validity[row >> 5] >> (row & 31)) & 1u) : true;
+      if (ok) {
+        key = (col.dtype == ANV_F32) ? make_key<uint32_t, float>(load_elem<float>(col.data, row))
+                                     : make_key<uint32_t, int32_t>(load_elem<int32_t>(col.data, row));
+        ok = key != PC_ZERO_KEY;
+      }
+    }
+  }
+  __shared__ uint32_t s_w[ANV_WARPS];
+  __shared__ unsigned long long s_base;
+  const uint32_t bal = __ballot_sync(ANV_FULL, ok);
+  if (lane == 0) s_w[warp] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int w = 0; w < ANV_WARPS; ++w) { const uint32_t t = s_w[w]; s_w[w] = acc; acc += t; }
+    s_base = acc ? atomicAdd(&S.state[c].n_valid, (unsigned long long)acc) : 0ull;
+  }
+  __syncthreads();
+  if (ok) S.buf[0][(size_t)c * S.stride + s_base + s_w[warp] + __popc(bal & ((1u << lane) - 1u))] = key;
+}
+
+// ---- split: splitters + lookup table of one column ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pc_split_kernel(const SortParams<uint32_t> S, const PcParams P) {
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const ColState& st = S.state[c];
+  const uint32_t* __restrict__ sorted = (st.cur ? S.buf[1] : S.buf[0]) + (size_t)c * S.stride;
+  const int64_t ms = (int64_t)st.n_valid;          // sample keys that survived (non-null, nonzero)
+  const int ns = P.P - 1;                          // splitters taken from the sample
+  auto sample_split = [&](int j) -> uint32_t {     // non-decreasing in j
+    if (ms == 0) return PC_ZERO_KEY;
+    int64_t idx = ((int64_t)(j + 1) * ms) / P.P;
+    if (idx >= ms) idx = ms - 1;
+    return sorted[idx];
+  };
+  int lo = 0, hi = ns;                             // z = number of sample splitters below the key of zero
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (sample_split(mid) < PC_ZERO_KEY) lo = mid + 1; else hi = mid; }
+  const int z = lo;
+  uint32_t* out = P.split + (size_t)c * P.NS;
+  for (int j = tid; j < ns; j += 256) { const uint32_t v = sample_split(j); out[j < z ? j : j + 1] = v; }
+  if (tid == 0) out[z] = PC_ZERO_KEY;
+  __syncthreads();
+  uint16_t* lut = P.lut + (size_t)c * (PC_LUT_CELLS + 1);
+  for (int q = tid; q <= PC_LUT_CELLS; q += 256) {
+    int a = 0, b = P.NS;
+    if (q == PC_LUT_CELLS) { a = P.NS; }
+    else {
+      const uint32_t v = (uint32_t)q << (32 - PC_LUT_BITS);
+      while (a < b) { const int mid = (a + b) >> 1; if (out[mid] < v) a = mid + 1; else b = mid; }
+    }
+    lut[q] = (uint16_t)a;
+  }
+}
+
+// ---- partition ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void pc_part_rows(const PcParams& P, const anv_column_t& col, const int c, const uint32_t* sS, const uint16_t* sL,
+                                             const int64_t r0, const int n_tile, unsigned long long& valid_acc) {
+  constexpr int VEC = 4, PER = SORT_TILE / ANV_BLOCK;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const T* __restrict__ data = reinterpret_cast<const T*>(col.data) + r0;
+  const uint32_t* __restrict__ vbits = col.validity;
+  const int row0 = tid * PER;
+  uint32_t keys[PER];
+  uint32_t okmask = 0;
+  if (row0 + PER <= n_tile) {
+    uint32_t vb = 0xFFFFu;
+    if (vbits) { const int64_t g = r0 + row0; vb = (__ldg(vbits + (g >> 5)) >> (g & 31)) & 0xFFFFu; }
+    okmask = vb;
+    const uint4* p = reinterpret_cast<const uint4*>(data + row0);
+#pragma unroll
+    for (int v = 0; v < PER / VEC; ++v) {
+      const uint4 q = ldg_stream(p + v);
+      T e[VEC];
+      unpack<T>(q, e);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) keys[v * VEC + i] = make_key<uint32_t, T>(e[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int row = row0 + i;
+      bool ok = row < n_tile;
+      keys[i] = 0;
+      if (ok) {
+        if (vbits) { const int64_t g = r0 + row; ok = (vbits[g >> 5] >> (g & 31)) & 1u; }
+        keys[i] = make_key<uint32_t, T>(data[row]);
+      }
+      okmask |= ok ? (1u << i) : 0u;
+    }
+  }
+  valid_acc += __popc(okmask);
+  uint32_t* __restrict__ cursor = P.cursor + (size_t)c * P.NB;
+  uint32_t* __restrict__ cnt_eq = P.cnt_eq + (size_t)c * P.NS;
+  uint32_t* __restrict__ slab = P.slab + (size_t)c * P.NB * P.cap;
+  bool over = false;
+#pragma unroll 4
+  for (int i = 0; i < PER; ++i) {
+    const bool ok = (okmask >> i) & 1u;
+    const uint32_t k = keys[i];
+    int lo = sL[k >> (32 - PC_LUT_BITS)], hi = sL[(k >> (32 - PC_LUT_BITS)) + 1];
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sS[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    const bool eq = ok && lo < P.NS && sS[lo] == k;
+    const uint32_t em = __ballot_sync(ANV_FULL, eq);
+    if (eq) {
+      const uint32_t peers = __match_any_sync(em, lo);
+      if (lane == __ffs(peers) - 1) atomicAdd(&cnt_eq[lo], (uint32_t)__popc(peers));
+    } else if (ok) {
+      const uint32_t pos = atomicAdd(&cursor[lo], 1u);
+      if (pos < P.cap) slab[(size_t)lo * P.cap + pos] = k;
+      else over = true;
+    }
+  }
+  if (over) P.st[c].overflow = 1;
+}
+
+__global__ void __launch_bounds__(ANV_BLOCK) pc_partition_kernel(const PcParams P) {
+  extern __shared__ __align__(16) uint32_t pc_sh[];
+  const int c = blockIdx.y, tid = threadIdx.x;
+  const anv_column_t col = P.cols[c];
+  uint32_t* sS = pc_sh;                                               // [NS]
+  uint16_t* sL = reinterpret_cast<uint16_t*>(pc_sh + ((P.NS + 3) & ~3));   // [PC_LUT_CELLS + 1]
+  {
+    const uint32_t* gS = P.split + (size_t)c * P.NS;
+    for (int i = tid; i < P.NS; i += ANV_BLOCK) sS[i] = gS[i];
+    const uint16_t* gL = P.lut + (size_t)c * (PC_LUT_CELLS + 1);
+    for (int i = tid; i <= PC_LUT_CELLS; i += ANV_BLOCK) sL[i] = gL[i];
+  }
+  __syncthreads();
+  unsigned long long valid_acc = 0;
+  const int64_t first = (int64_t)blockIdx.x * PC_TILES_PER_CTA;
+  for (int t = 0; t < PC_TILES_PER_CTA; ++t) {
+    const int64_t r0 = (first + t) * SORT_TILE;
+    if (r0 >= P.n_rows) break;
+    const int n_tile = (int)min((int64_t)SORT_TILE, P.n_rows - r0);
+    if (col.dtype == ANV_F32) pc_part_rows<float>(P, col, c, sS, sL, r0, n_tile, valid_acc);
+    else pc_part_rows<int32_t>(P, col, c, sS, sL, r0, n_tile, valid_acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid_acc += __shfl_down_sync(ANV_FULL, valid_acc, o);
+  if ((tid & 31) == 0 && valid_acc) atomicAdd(&P.st[c].n_valid, valid_acc);
+}
+
+// ---- cum: total order of the column from the interleaved counts; rank queries; splitter contributions ---------------------
+__global__ void __launch_bounds__(1024) pc_cum_kernel(const PcParams P, const int64_t* ranks, const int n_ranks, double* rank_values) {
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PcCol& st = P.st[c];
+  const uint32_t* cursor = P.cursor + (size_t)c * P.NB;
+  const uint32_t* cnt_eq = P.cnt_eq + (size_t)c * P.NS;
+  const uint32_t* S = P.split + (size_t)c * P.NS;
+  uint32_t* cum = P.cum + (size_t)c * 2 * P.NB;
+  const int n_ent = 2 * P.NB - 1;                                     // lt_0, eq_0, lt_1, ..., eq_{NS-1}, lt_NS
+  const int per = (n_ent + 1023) / 1024;
+  const int e0 = tid * per, e1 = min(e0 + per, n_ent);
+  auto entry = [&](int e) -> uint32_t { return (e & 1) ? cnt_eq[e >> 1] : min(cursor[e >> 1], P.cap); };
+  unsigned long long run = 0, eq_distinct = 0, best = 0;
+  bool over = false;
+  for (int e = e0; e < e1; ++e) {
+    run += entry(e);
+    if (e & 1) {
+      const uint32_t n = cnt_eq[e >> 1];
+      if (n) { ++eq_distinct; const unsigned long long cand = ((unsigned long long)n << 32) | (uint32_t)~S[e >> 1]; if (cand > best) best = cand; }
+    } else if (cursor[e >> 1] > P.cap) over = true;
+  }
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long wbest[32], wdist[32];
+  unsigned long long inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(ANV_FULL, inc, o); if (lane >= o) inc += t; }
+  unsigned long long rb = best, rd = eq_distinct;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ob = __shfl_down_sync(ANV_FULL, rb, o); if (ob > rb) rb = ob;
+    rd += __shfl_down_sync(ANV_FULL, rd, o);
+  }
+  if (lane == 31) wsum[warp] = inc;
+  if (lane == 0) { wbest[warp] = rb; wdist[warp] = rd; }
+  if (over) st.overflow = 1;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long w = wsum[lane];
+    unsigned long long wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(ANV_FULL, wi, o); if (lane >= o) wi += t; }
+    wsum[lane] = wi - w;
+    unsigned long long b2 = wbest[lane], d2 = wdist[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ob = __shfl_down_sync(ANV_FULL, b2, o); if (ob > b2) b2 = ob;
+      d2 += __shfl_down_sync(ANV_FULL, d2, o);
+    }
+    if (lane == 0) { if (b2) atomicMax(&st.best, b2); if (d2) atomicAdd(&st.distinct, d2); }
+  }
+  __syncthreads();
+  unsigned long long acc = wsum[warp] + inc - run;
+  for (int e = e0; e < e1; ++e) { acc += entry(e); cum[e] = (uint32_t)acc; }
+  __syncthreads();
+  // rank queries: first entry whose inclusive prefix reaches the rank
+  if (tid < n_ranks) {
+    const int64_t rk = ranks[(size_t)c * n_ranks + tid];
+    const unsigned long long total = n_ent > 0 ? cum[n_ent - 1] : 0;
+    double v = nan("");
+    if (rk > 0 && (unsigned long long)rk <= total) {
+      int lo = 0, hi = n_ent - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if ((unsigned long long)cum[mid] < (unsigned long long)rk) lo = mid + 1; else hi = mid; }
+      if (lo & 1) {
+        v = sorted_key_to_double((uint64_t)S[lo >> 1] << 32, P.cols[c].dtype);
+      } else {
+        const int q = atomicAdd(&st.n_queries, 1);
+        st.q_bucket[q] = lo >> 1;
+        st.q_local[q] = (uint32_t)(rk - (lo ? cum[lo - 1] : 0));
+        st.q_slot[q] = tid;
+      }
+    }
+    rank_values[(size_t)c * n_ranks + tid] = v;
+  }
+}
+
+// ---- count: one CTA per bucket ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ANV_BLOCK) pc_count_kernel(const PcParams P, const int n_ranks, double* rank_values) {
+  const int c = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+  PcCol& st = P.st[c];
+  const uint32_t n = min(P.cursor[(size_t)c * P.NB + b], P.cap);
+  if (n == 0) return;                                   // (uniform: the cursors are final when this kernel starts)
+  extern __shared__ __align__(16) uint32_t pc_tab[];
+  uint32_t* tkey = pc_tab;
+  uint32_t* tcnt = pc_tab + PC_SLOTS;
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_sel[2];
+  const uint32_t* __restrict__ keys = P.slab + ((size_t)c * P.NB + b) * P.cap;
+  const uint32_t sweeps = (n + PC_SWEEP_KEYS - 1) / PC_SWEEP_KEYS;
+  unsigned long long best = 0;
+  uint32_t distinct = 0;
+  bool full = false;
+  for (uint32_t sw = 0; sw < sweeps; ++sw) {
+    for (int i = tid; i < PC_SLOTS; i += ANV_BLOCK) { tkey[i] = PC_ZERO_KEY; tcnt[i] = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += ANV_BLOCK) {
+      const uint32_t k = keys[i];
+      if (sweeps > 1 && ((k * 0x85EBCA6Bu) >> 12) % sweeps != sw) continue;
+      uint32_t slot = (k * 0x9E3779B1u) >> (32 - PC_SLOTS_LOG);
+      int probes = 0;
+      while (true) {
+        const uint32_t prev = atomicCAS(&tkey[slot], PC_ZERO_KEY, k);
+        if (prev == PC_ZERO_KEY || prev == k) { atomicAdd(&tcnt[slot], 1u); break; }
+        slot = (slot + 1) & (PC_SLOTS - 1);
+        if (++probes >= PC_SLOTS) { full = true; break; }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < PC_SLOTS; i += ANV_BLOCK) {
+      const uint32_t cnt = tcnt[i];
+      if (cnt) {
+        ++distinct;
+        const unsigned long long cand = ((unsigned long long)cnt << 32) | (uint32_t)~tkey[i];
+        if (cand > best) best = cand;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ob = __shfl_down_sync(ANV_FULL, best, o); if (ob > best) best = ob;
+    distinct += __shfl_down_sync(ANV_FULL, distinct, o);
+  }
+  if ((tid & 31) == 0) {
+    if (best) atomicMax(&st.best, best);
+    if (distinct) atomicAdd(&st.distinct, (unsigned long long)distinct);
+  }
+  if (full) st.overflow = 1;
+  // requested ranks inside this bucket: 4-pass radix select over the bucket's keys (L2-resident)
+  const int nq = st.n_queries;
+  for (int q = 0; q < nq; ++q) {
+    if (st.q_bucket[q] != b) continue;                     // uniform across the CTA
+    uint32_t prefix = 0, r = st.q_local[q];
+    for (int pass = 3; pass >= 0; --pass) {
+      s_hist[tid] = 0;
+      __syncthreads();
+      const int sh = pass * 8;
+      for (uint32_t i = tid; i < n; i += ANV_BLOCK) {
+        const uint32_t k = keys[i];
+        if (pass == 3 || ((k ^ prefix) >> (sh + 8)) == 0) atomicAdd(&s_hist[(k >> sh) & 0xFFu], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t acc = 0, d = 0;
+        for (; d < 255; ++d) { if (acc + s_hist[d] >= r) break; acc += s_hist[d]; }
+        s_sel[0] = d; s_sel[1] = r - acc;
+      }
+      __syncthreads();
+      prefix |= s_sel[0] << sh;
+      r = s_sel[1];
+      __syncthreads();
+    }
+    if (tid == 0) rank_values[(size_t)c * n_ranks + st.q_slot[q]] = sorted_key_to_double((uint64_t)prefix << 32, P.cols[c].dtype);
+  }
+}
+
+__global__ void pc_final_kernel(const PcParams P, double* mode_value, int64_t* mode_rows, int64_t* n_distinct) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_cols) return;
+  const PcCol& st = P.st[c];
+  if (st.overflow) { mode_value[c] = nan(""); mode_rows[c] = -2; n_distinct[c] = -2; return; }   // redo on the LSD path
+  if (st.n_valid == 0 || st.best == 0) { mode_value[c] = nan(""); mode_rows[c] = 0; n_distinct[c] = 0; return; }
+  const uint32_t key = ~(uint32_t)(st.best & 0xFFFFFFFFull);
+  mode_value[c] = sorted_key_to_double((uint64_t)key << 32, P.cols[c].dtype);
+  mode_rows[c] = (int64_t)(st.best >> 32);
+  n_distinct[c] = (int64_t)st.distinct;
+}
+
+struct PcLayout {
+  int P, NS, NB;
+  uint32_t cap;
+  int64_t m;
+  size_t lsd, split, lut, cursor, cnt_eq, cum, st, slab, total;
+  PcLayout(int n_cols, int64_t n_rows) {
+    int p = 256;
+    while (p < 16384 && (int64_t)p * 3072 < n_rows) p <<= 1;
+    P = p; NS = p; NB = p + 1;
+    m = (int64_t)PC_OVERSAMPLE * p;
+    if (m > n_rows) m = n_rows > 0 ? n_rows : 1;
+    const int64_t mean = n_rows / p + 1;
+    cap = (uint32_t)(((4 * mean + 1024) + 7) & ~(int64_t)7);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+    lsd = take(Layout<uint32_t>(n_cols, m).total);
+    split = take((size_t)n_cols * NS * 4);
+    lut = take((size_t)n_cols * (PC_LUT_CELLS + 1) * 2);
+    cursor = take((size_t)n_cols * NB * 4);
+    cnt_eq = take((size_t)n_cols * NS * 4);
+    cum = take((size_t)n_cols * 2 * NB * 4);
+    st = take((size_t)n_cols * sizeof(PcCol));
+    slab = take((size_t)n_cols * NB * cap * 4);
+    total = o + 256;
+  }
+};
+
+static int run_partition_count(const anv_column_t* cols, int n_cols, int64_t n_rows, double* mode_value, int64_t* mode_rows,
+                               int64_t* n_distinct, const int64_t* ranks, int n_ranks, double* rank_values, void* workspace,
+                               size_t workspace_bytes, cudaStream_t st) {
+  PcLayout L(n_cols, n_rows);
+  if (workspace_bytes < L.total) { set_error("anv_mode_distinct_partition: workspace too small (%zu < %zu)", workspace_bytes, L.total); return ANV_ERR_WORKSPACE; }
+  char* w = reinterpret_cast<char*>(workspace);
+  // --- the sample sort reuses the LSD machinery on m keys per column ---
+  Layout<uint32_t> LS(n_cols, L.m);
+  char* ws = w + L.lsd;
+  SortParams<uint32_t> S{};
+  S.cols = cols; S.n_cols = n_cols; S.n_rows = L.m;
+  S.stride = (L.m + 63) & ~(int64_t)63;
+  S.n_tiles = (int)((L.m + SORT_TILE - 1) / SORT_TILE);
+  if (S.n_tiles < 1) S.n_tiles = 1;
+  S.buf[0] = reinterpret_cast<uint32_t*>(ws + LS.buf0);
+  S.buf[1] = reinterpret_cast<uint32_t*>(ws + LS.buf1);
+  S.state = reinterpret_cast<ColState*>(ws + LS.state);
+  S.tile_hist = reinterpret_cast<uint32_t*>(ws + LS.tile_hist);
+  S.summ = reinterpret_cast<TileSummary<uint32_t>*>(ws + LS.summ);
+  PcParams P{};
+  P.cols = cols; P.n_cols = n_cols; P.n_rows = n_rows; P.P = L.P; P.NS = L.NS; P.NB = L.NB; P.cap = L.cap; P.m = L.m;
+  P.split = reinterpret_cast<uint32_t*>(w + L.split);
+  P.lut = reinterpret_cast<uint16_t*>(w + L.lut);
+  P.cursor = reinterpret_cast<uint32_t*>(w + L.cursor);
+  P.cnt_eq = reinterpret_cast<uint32_t*>(w + L.cnt_eq);
+  P.cum = reinterpret_cast<uint32_t*>(w + L.cum);
+  P.st = reinterpret_cast<PcCol*>(w + L.st);
+  P.slab = reinterpret_cast<uint32_t*>(w + L.slab);
+  ANV_CUDA(cudaMemsetAsync(S.state, 0, (size_t)n_cols * sizeof(ColState), st));
+  ANV_CUDA(cudaMemsetAsync(w + L.cursor, 0, L.st + (size_t)n_cols * sizeof(PcCol) - L.cursor, st));   // cursor, cnt_eq, cum, st
+  {
+    dim3 grid((unsigned)((L.m + ANV_BLOCK - 1) / ANV_BLOCK), n_cols);
+    pc_sample_kernel<<<grid, ANV_BLOCK, 0, st>>>(S, n_rows, L.m);
+    ANV_CUDA(cudaGetLastError());
+    dim3 tg(S.n_tiles, n_cols);
+    for (int pass = 0; pass < 4; ++pass) {
+      S.pass = pass;
+      sort_hist_kernel<uint32_t><<<tg, ANV_BLOCK, 0, st>>>(S);
+      sort_scan_kernel<uint32_t><<<n_cols, 1024, 0, st>>>(S);
+      sort_scatter_kernel<uint32_t><<<tg, SCAT_THREADS, 0, st>>>(S);
+      ANV_CUDA(cudaGetLastError());
+    }
+    pc_split_kernel<<<n_cols, 256, 0, st>>>(S, P);
+    ANV_CUDA(cudaGetLastError());
+  }
+  {
+    const size_t smem = (size_t)((L.NS + 3) & ~3) * 4 + (size_t)(PC_LUT_CELLS + 1) * 2 + 16;
+    static bool attr_done = false;
+    if (!attr_done) {
+      ANV_CUDA(cudaFuncSetAttribute(pc_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      ANV_CUDA(cudaFuncSetAttribute(pc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SLOTS * 8));
+      attr_done = true;
+    }
+    const int64_t tiles = (n_rows + SORT_TILE - 1) / SORT_TILE;
+    dim3 grid((unsigned)((tiles + PC_TILES_PER_CTA - 1) / PC_TILES_PER_CTA), n_cols);
+    if (tiles > 0) pc_partition_kernel<<<grid, ANV_BLOCK, smem, st>>>(P);
+    ANV_CUDA(cudaGetLastError());
+  }
+  pc_cum_kernel<<<n_cols, 1024, 0, st>>>(P, ranks, n_ranks, rank_values);
+  ANV_CUDA(cudaGetLastError());
+  {
+    dim3 grid(L.NB, n_cols);
+    pc_count_kernel<<<grid, ANV_BLOCK, PC_SLOTS * 8, st>>>(P, n_ranks, rank_values);
+    ANV_CUDA(cudaGetLastError());
+  }
+  pc_final_kernel<<<(n_cols + 127) / 128, 128, 0, st>>>(P, mode_value, mode_rows, n_distinct);
+  ANV_CUDA(cudaGetLastError());
+  return ANV_OK;
+}
+
 }  // namespace anv
 
 using namespace anv;
@@ -700,4 +1186,22 @@ extern "C" int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n
   cudaStream_t st = (cudaStream_t)stream;
   if (key_bits == 32) return run_mode_distinct<uint32_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, workspace, workspace_bytes, st);
   return run_mode_distinct<uint64_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, workspace, workspace_bytes, st);
+}
+
+extern "C" size_t anv_mode_distinct_partition_workspace_bytes(int n_cols, int64_t n_rows) {
+  if (n_cols <= 0 || n_rows < 0) return 256;
+  return PcLayout(n_cols, n_rows).total;
+}
+
+extern "C" int anv_mode_distinct_partition(const anv_column_t* cols, int n_cols, int64_t n_rows, double* mode_value,
+                                           int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks, int n_ranks,
+                                           double* rank_values, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_ranks < 0 || n_ranks > PC_MAX_RANKS || (n_ranks > 0 && (!ranks || !rank_values))) { set_error("anv_mode_distinct_partition: bad ranks arguments (n_ranks <= 16)"); return ANV_ERR_INVALID; }
+  if (n_cols < 0 || n_rows < 0) { set_error("anv_mode_distinct_partition: bad arguments"); return ANV_ERR_INVALID; }
+  if (n_cols == 0) return ANV_OK;
+  if (n_cols > 65535) { set_error("n_cols > 65535"); return ANV_ERR_UNSUPPORTED; }
+  if (n_rows >= ((int64_t)1 << 32)) { set_error("anv_mode_distinct_partition: n_rows >= 2^32 per call is not supported"); return ANV_ERR_UNSUPPORTED; }
+  if (!cols || !mode_value || !mode_rows || !n_distinct || !workspace) { set_error("anv_mode_distinct_partition: NULL argument"); return ANV_ERR_INVALID; }
+  return run_partition_count(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
 }

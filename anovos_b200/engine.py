@@ -375,17 +375,31 @@ def select_ranks(frame: ColumnFrame, names, ranks):
 # ---- sort-based exact mode / distinct --------------------------------------------------------
 
 SORT_WORKSPACE_BUDGET = 24 << 30  # bytes of scratch one sort batch may use
+PARTITION_MIN_ROWS = 1 << 18      # below this the LSD sort is launch-bound anyway and needs no sampling
+sort_algorithm = "auto"           # "auto" | "lsd" | "partition" (tests force one or the other)
+
+
+def _mode_distinct_batches(frame, idxs, names, per_col_bytes):
+    torch = _lib.require_cuda()
+    budget = SORT_WORKSPACE_BUDGET
+    if per_col_bytes * len(idxs) > (4 << 30):  # cudaMemGetInfo costs ~7 ms: only ask when the scratch is large
+        budget = min(budget, int(torch.cuda.mem_get_info()[0] * 0.8))
+    batch = max(1, min(len(idxs), budget // max(per_col_bytes, 1)))
+    for b0 in range(0, len(idxs), batch):
+        sub_i = idxs[b0:b0 + batch]
+        yield sub_i, [names[i] for i in sub_i]
 
 
 def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
     """-> list of (mode value | None, mode_rows | None, n_distinct) for NUMERIC columns.
     ranks: optional int64 [n_cols, n_ranks] of 1-based ranks among the non-null values (0 = skip);
-    then returns (list, float64 [n_cols, n_ranks]) with the exact order statistics read from the
-    sorted keys."""
+    then returns (list, float64 [n_cols, n_ranks]) with the exact order statistics.
+    32-bit columns of >= PARTITION_MIN_ROWS rows take the partition + count path (anv_mode_distinct_partition: no
+    sort); the others - and any column that path hands back (mode_rows == -2) - the LSD radix sort."""
     if getattr(frame, "is_partitioned", False):
         return frame.sort_mode_distinct(names, ranks)
     global launch_count
-    torch = _lib.require_cuda()
+    _lib.require_cuda()
     L = _lib.lib()
     names = list(names)
     n_ranks = 0
@@ -398,35 +412,52 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
     for i, nme in enumerate(names):
         kb = 32 if frame.column(nme).anv_dtype in (_lib.ANV_F32, _lib.ANV_I32) else 64
         groups.setdefault(kb, []).append(i)
-    for kb, idxs in groups.items():
-        per_col = L.anv_mode_distinct_workspace_bytes(1, frame.n_rows, kb)
-        budget = SORT_WORKSPACE_BUDGET
-        if per_col * len(idxs) > (4 << 30):  # cudaMemGetInfo costs ~7 ms: only ask when the scratch is large
-            budget = min(budget, int(torch.cuda.mem_get_info()[0] * 0.8))
-        batch = max(1, min(len(idxs), budget // max(per_col, 1)))
-        for b0 in range(0, len(idxs), batch):
-            sub_i = idxs[b0:b0 + batch]
-            sub = [names[i] for i in sub_i]
+
+    def run(kb, idxs, partition):
+        global launch_count
+        redo = []
+        per_col = (L.anv_mode_distinct_partition_workspace_bytes(1, frame.n_rows) if partition
+                   else L.anv_mode_distinct_workspace_bytes(1, frame.n_rows, kb))
+        for sub_i, sub in _mode_distinct_batches(frame, idxs, names, per_col):
             desc, keep = frame.descriptors(sub)
-            ws_bytes = L.anv_mode_distinct_workspace_bytes(len(sub), frame.n_rows, kb)
-            ws = _dev_bytes(ws_bytes)
             n = len(sub)
+            ws_bytes = (L.anv_mode_distinct_partition_workspace_bytes(n, frame.n_rows) if partition
+                        else L.anv_mode_distinct_workspace_bytes(n, frame.n_rows, kb))
+            ws = _dev_bytes(ws_bytes)
             mv, mr, nd = _dev_bytes(n * 8), _dev_bytes(n * 8), _dev_bytes(n * 8)
             drk = _to_dev(ranks[sub_i]) if n_ranks else None
             drv = _dev_bytes(n * n_ranks * 8) if n_ranks else None
-            _call(L.anv_mode_distinct, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv.data_ptr(), mr.data_ptr(),
-                  nd.data_ptr(), drk.data_ptr() if drk is not None else None, n_ranks,
-                  drv.data_ptr() if drv is not None else None, ws.data_ptr(), ws_bytes, _stream(),
-                  nbytes=input_bytes(frame, sub))
-            launch_count += 3 + 3 * (kb // 8)
+            common = (drk.data_ptr() if drk is not None else None, n_ranks, drv.data_ptr() if drv is not None else None,
+                      ws.data_ptr(), ws_bytes, _stream())
+            if partition:
+                _call(L.anv_mode_distinct_partition, "anv_mode_distinct_partition", desc.data_ptr(), n, frame.n_rows, mv.data_ptr(),
+                      mr.data_ptr(), nd.data_ptr(), *common, nbytes=input_bytes(frame, sub))
+                launch_count += 6 + 12
+            else:
+                _call(L.anv_mode_distinct, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv.data_ptr(), mr.data_ptr(),
+                      nd.data_ptr(), *common, nbytes=input_bytes(frame, sub))
+                launch_count += 3 + 3 * (kb // 8)
             hv = _host(mv).view(np.float64)[:n]
             hr = _host(mr).view(np.int64)[:n]
             hd = _host(nd).view(np.int64)[:n]
-            if n_ranks:
-                rvals[sub_i] = _host(drv).view(np.float64)[:n * n_ranks].reshape(n, n_ranks)
+            hrv = _host(drv).view(np.float64)[:n * n_ranks].reshape(n, n_ranks) if n_ranks else None
             del ws
-            for j, nme in enumerate(sub):
+            for j, (i, nme) in enumerate(zip(sub_i, sub)):
+                if hr[j] == -2:           # a bucket overflowed (sampling failure): this column goes through the sort
+                    redo.append(i)
+                    continue
+                if n_ranks:
+                    rvals[i] = hrv[j]
                 res[nme] = (float(hv[j]), int(hr[j]), int(hd[j])) if hr[j] > 0 else (None, None, 0)
+        return redo
+
+    for kb, idxs in groups.items():
+        use_partition = (kb == 32 and n_ranks <= 16 and sort_algorithm != "lsd"
+                         and (sort_algorithm == "partition" or frame.n_rows >= PARTITION_MIN_ROWS))
+        if use_partition:
+            idxs = run(kb, idxs, True)
+        if idxs:
+            run(kb, idxs, False)
     out = [res[n] for n in names]
     return (out, rvals) if ranks is not None else out
 

@@ -53,6 +53,11 @@ CPU_SAMPLE_ROWS = 1_000_000
 SORT_WORDS_PER_KEY = 1 + 4 * 3 + 1
 SORT_DESIGN = ("batched 8-bit LSD radix sort + run summaries (anv_mode_distinct: pack, 4 x {sort_hist, sort_scan, sort_scatter}, "
                "run_tile, run_merge) - exact mode / distinct / percentiles")
+# the partition + count path (anv_mode_distinct_partition, 32-bit columns): one read of the column, then every key that is not
+# a splitter value (zeros and heavy hitters are only counted) is written once to its bucket and read once by the counting CTA
+PARTITION_WORDS_PER_KEY = 2
+PARTITION_DESIGN = ("partition + count (anv_mode_distinct_partition: sample, split, pc_partition_kernel, pc_cum_kernel, pc_count_kernel) - "
+                    "exact mode / distinct / percentiles without sorting")
 
 
 
@@ -163,7 +168,8 @@ KERNEL_NAMES = {
     "anv_moments_hist": "scan_kernel<MOM+HIST> (anv_moments_hist: moments + histogram in one read)",
 }
 # what limits each call (ncu evidence under profiles/): the roofline fraction is always quoted against HBM
-BOUND = {"anv_mode_distinct": "issue", "anv_hll_registers": "issue", "anv_moments_hist": "issue"}
+BOUND = {"anv_mode_distinct": "issue", "anv_mode_distinct_partition": "l2 (per-key atomics and 4-byte stores)", "anv_hll_registers": "issue",
+         "anv_moments_hist": "issue"}
 
 
 def _run_ours(args, out):
@@ -271,9 +277,12 @@ def _run_ours(args, out):
         alg = v["input_bytes"] / args.steps
         if call == "anv_mode_distinct":
             alg += n_keys * 4 * SORT_WORDS_PER_KEY
+        elif call == "anv_mode_distinct_partition":
+            alg += n_keys * 4 * PARTITION_WORDS_PER_KEY
         ach = alg / (ms_step * 1e-3) / 1e9 if (alg and ms_step > 0) else None
         traffic = traffic_tbl.get(call)
-        return {"kernel": KERNEL_NAMES.get(call, SORT_DESIGN if call == "anv_mode_distinct" else call), "call": call,
+        return {"kernel": KERNEL_NAMES.get(call, {"anv_mode_distinct": SORT_DESIGN, "anv_mode_distinct_partition": PARTITION_DESIGN}.get(call, call)),
+                "call": call,
                 "bound": BOUND.get(call, "hbm"), "achieved": ach, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak if ach else None,
                 "traffic": traffic / per_step if traffic else None, "traffic_source": traffic_src if traffic else None,
@@ -282,7 +291,7 @@ def _run_ours(args, out):
                 "share_of_step": v["ms"] / ms if ms > 0 else None}
     by_share = sorted(kt, key=lambda c: -kt[c]["ms"])
     roofline = roof(by_share[0]) if by_share else None
-    if roofline is not None and roofline["bound"] == "issue":
+    if roofline is not None and roofline["bound"] != "hbm":
         roofline["note"] = ("bound by instruction issue, not by HBM (ncu: profiles/); frac is still achieved algorithmic GB/s over the "
                             "measured HBM peak - see roofline_kernels for the HBM-bound scan kernels the step also runs")
     roofline_kernels = [roof(c) for c in by_share[1:]]
@@ -324,8 +333,8 @@ def _run_ours(args, out):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (on-device Philox4x32-10, bit-identical NumPy twin: normal/lognormal/uniform/zero-inflated "
-                        "float32, null rates 0/0.1%/2%/30%%%s)" % (", every 4th column a Zipf(1.2) string column of cardinality 2/12/100/10000"
-                                                                  if cat_every else ""),
+                        "float32, null rates 0 / 0.1 / 2 / 30 percent" +
+                        (", every 4th column a Zipf(1.2) string column of cardinality 2/12/100/10000)" if cat_every else ")"),
                 "config": {"workload": args.workload + ": " + wl["desc"], "rows": rows, "cols_per_gpu": cols,
                            "numeric_cols_per_gpu": len(num), "categorical_cols_per_gpu": cols - len(num),
                            "l2": "inputs (%.1f GB per GPU) are larger than L2" % (rows * cols * 4 / 1e9),

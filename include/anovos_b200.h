@@ -189,6 +189,16 @@ int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, int 
                       double* mode_value, int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks,
                       int n_ranks, double* rank_values, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same results for F32 / I32 columns WITHOUT sorting them (sort.cu, "partition + count"): sample -> splitters ->
+ * one partition pass over the raw column (keys equal to a splitter - zeros, heavy hitters, discrete values - are only
+ * counted) -> per-bucket shared-memory hash tables (multiplicities) and in-bucket radix select for the requested ranks.
+ * About 3 words of HBM traffic per key instead of ~14.  A column whose bucket overflows (sampling failure; probability
+ * negligible) comes back with mode_rows = n_distinct = -2: redo it with anv_mode_distinct.  n_ranks <= 16. */
+size_t anv_mode_distinct_partition_workspace_bytes(int n_cols, int64_t n_rows);
+int anv_mode_distinct_partition(const anv_column_t* cols, int n_cols, int64_t n_rows, double* mode_value,
+                                int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks, int n_ranks,
+                                double* rank_values, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Spark's Bernoulli row sampler (the DEFAULT path of drift_detector.statistics: use_sampling=True ->
  *      data_sampling.py:122-149 `idf.sample(False, fraction, seed)` / `stat.sampleBy("merge", fractions, seed)`,
  *      drift_detector.py:187-211).  One partition per call: Spark seeds XORShiftRandom with seed + partitionIndex,

@@ -201,8 +201,18 @@ def test_select_ranks_exact(n):
     assert np.array_equal(got, np.array(exp), equal_nan=True)   # exact order statistics
 
 
+@pytest.fixture(params=["lsd", "partition"])
+def sort_algo(request):
+    """Both implementations of the exact mode / distinct / order-statistic path: the LSD radix sort and the partition +
+    count path (forced here also at sizes where "auto" would sort)."""
+    from anovos_b200 import engine
+    old, engine.sort_algorithm = engine.sort_algorithm, request.param
+    yield request.param
+    engine.sort_algorithm = old
+
+
 @pytest.mark.parametrize("n", [1, 40, 5000, 200001])
-def test_mode_distinct_exact(n):
+def test_mode_distinct_exact(n, sort_algo):
     from anovos_b200 import engine
     from anovos_b200.frame import ColumnFrame
     rng = np.random.default_rng(n)
@@ -303,3 +313,64 @@ def test_moments_hist_without_early_pivot():
         exp = S.assign_bins(vals.astype(np.float64), valid, cuts[i], 10)
         assert np.array_equal(h[i, :11], np.bincount(exp, minlength=11).astype(np.uint64)), nme
         assert m2["min"][i] == m["min"][i] and m2["max"][i] == m["max"][i] and m2["n_nonzero"][i] == m["n_nonzero"][i]
+
+
+@pytest.mark.parametrize("n", [300_007, 3_000_001])
+def test_partition_count_adversarial_columns(n):
+    """The partition + count path on the inputs that stress it: heavy hitters below and above the splitter threshold,
+    discrete columns (every key equals a splitter), a constant column, an all-null column, NaN runs, keys on both sides of
+    zero, near-constant columns with a few outliers, sorted input (the sample positions are stratified) - against NumPy,
+    and cell for cell against the LSD sort."""
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    rng = np.random.default_rng(n)
+    heavy = rng.normal(0, 1, n).astype(np.float32)
+    heavy[rng.random(n) < 0.2] = 1.25                      # 20 % one value
+    heavy[rng.random(n) < 0.0003] = -7.5                   # ~ 1/P of the rows: may or may not become a splitter
+    nanny = rng.normal(5, 2, n).astype(np.float32)
+    nanny[rng.random(n) < 0.1] = np.nan
+    spike = np.full(n, 3.0, np.float32)
+    spike[rng.integers(0, n, 50)] = rng.normal(0, 1e6, 50).astype(np.float32)
+    cols = {
+        "normal": pa.array(rng.normal(27, 9, n).astype(np.float32)),
+        "heavy": pa.array(heavy, mask=rng.random(n) < 0.01),
+        "ints_small": pa.array(rng.integers(-3, 4, n).astype(np.int32)),
+        "ints_wide": pa.array(rng.integers(-2 ** 31, 2 ** 31 - 1, n).astype(np.int32), mask=rng.random(n) < 0.3),
+        "constant": pa.array(np.full(n, -4.5, np.float32)),
+        "all_null": pa.array(np.zeros(n, np.float32), mask=np.ones(n, bool)),
+        "nan_runs": pa.array(nanny),
+        "spike": pa.array(spike),
+        "sorted": pa.array(np.sort(rng.exponential(3, n)).astype(np.float32)),
+        "zero_inflated": pa.array(np.where(rng.random(n) < 0.7, 0.0, rng.exponential(2, n)).astype(np.float32), mask=rng.random(n) < 0.3),
+        "lognormal": pa.array(np.exp(rng.normal(0, 0.75, n)).astype(np.float32)),
+    }
+    t = pa.table(cols)
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    probs = [0.0001, 0.01, 0.05, 0.1, 0.25, 0.5, 0.75, 0.9, 0.95, 0.99, 1.0]
+    rk = np.array([engine.quantile_ranks(n - t.column(c).null_count, probs) for c in names])
+    old = engine.sort_algorithm
+    try:
+        engine.sort_algorithm = "partition"
+        got, qv = engine.sort_mode_distinct(fr, names, rk)
+        engine.sort_algorithm = "lsd"
+        ref, qr = engine.sort_mode_distinct(fr, names, rk)
+    finally:
+        engine.sort_algorithm = old
+    assert got == ref
+    assert np.array_equal(qv, qr, equal_nan=True)
+    for i, c in enumerate(names):
+        vals, valid = S.column_values(t, c)
+        x = vals[valid]
+        if x.size == 0:
+            assert got[i] == (None, None, 0)
+            continue
+        srt = np.sort(x.astype(np.float64))              # NaN last, like Spark
+        exp = [srt[r - 1] if r else np.nan for r in rk[i]]
+        assert np.array_equal(qv[i], np.array(exp), equal_nan=True), c
+        if x.dtype.kind == "f":
+            x = x + 0.0
+        u, k = np.unique(x, return_counts=True)          # equal_nan: all NaNs are one value
+        assert got[i][2] == u.size and got[i][1] == int(k.max()), c
+        best = u[k == k.max()]
+        assert got[i][0] == float(np.nanmin(best)) or (np.isnan(got[i][0]) and np.isnan(best).all()), c
