@@ -353,11 +353,12 @@ def outlier_detection(spark, idf, list_of_cols="all", drop_cols=[], detection_si
         methods, n_val = _outlier_methodologies(detection_side, cfg)
         cfg["min_validation"] = n_val
         sample = fr
-        if fr.count() > sample_size:     # thresholds from a Bernoulli sample (:832-838; Spark's sampler is not reproducible)
-            if getattr(fr, "is_partitioned", False):
-                raise NotImplementedError("sampling a row-partitioned frame is not implemented: raise sample_size")
-            from ..drift_stability.drift_detector import _sample
-            sample = _sample(fr.select(cols), sample_size / fr.count(), 11)
+        if fr.count() > sample_size:
+            # thresholds from a Bernoulli sample (:832-838): `idf.sample(sample_size / idf_count, False, 11)`.  With a float in
+            # first position pyspark shifts the arguments (withReplacement omitted): fraction = the float, seed = int(False)
+            # = 0, and the 11 is dropped - so Spark's XORShiftRandom stream is seeded with 0 (+ partition index).
+            from ..data_ingest.data_sampling import data_sample
+            sample = data_sample(fr.select(cols), fraction=sample_size / fr.count(), method_type="random", seed_value=0)
         cols, params, skewed = _outlier_bounds(sample, cols, detection_side, cfg, methods, n_val)
         if model_path != "NA":
             sk = {"lower": ["skewed_attribute", None], "upper": [None, "skewed_attribute"]}.get(
@@ -389,10 +390,22 @@ def outlier_detection(spark, idf, list_of_cols="all", drop_cols=[], detection_si
                 for b, f in enumerate(flags_of_bin, start=1):
                     if f:
                         flag[ids[i] == b] = f
+                dcol = fr.column(c).device()[0]
+                if dcol.is_floating_point():       # the binning kernels put NaN in the last bin; `(v - upper) > 0` is
+                    flag[dcol != dcol] = 0         # False for NaN in the reference's compare (:937-966): never an outlier
                 lower_n, upper_n = int((flag == -1).sum()), int((flag == 1).sum())
             else:
                 lower_n = sum(int(hist[i, b]) for b, f in enumerate(flags_of_bin, start=1) if f == -1)
                 upper_n = sum(int(hist[i, b]) for b, f in enumerate(flags_of_bin, start=1) if f == 1)
+                if flags_of_bin[-1] == 1 and fr.column(c).anv_dtype in (_lib.ANV_F32, _lib.ANV_F64):
+                    nan_rows = 0                   # NaN values sit in the last bin: not outliers (see above)
+                    for ch in (fr.chunks([c]) if getattr(fr, "is_partitioned", False) else [fr]):
+                        dch, vch = ch.column(c).device()
+                        isn = dch != dch
+                        if vch is not None:
+                            isn &= ch.valid_mask(c)
+                        nan_rows += int(isn.sum())
+                    upper_n -= nan_rows
             rows.append((c, lower_n, upper_n, 0))
             if not need_rows:
                 continue

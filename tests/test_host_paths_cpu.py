@@ -267,3 +267,33 @@ def test_saved_frequency_round_trip_keeps_string_keys(tmp_path):
     _close_cols(again, direct, ["PSI", "HD", "JSD", "KS"])
     f = pd.read_csv(tmp_path / "m" / "drift_statistics" / "frequency_counts" / "s" / "part-00000.csv", dtype=str, keep_default_na=False)
     assert sorted(k for k in f["s"] if k != "") == sorted(cats)
+
+
+def test_outlier_nan_values_are_not_outliers(tmp_path):
+    """`(v - upper) > 0` is False for NaN in the reference's compare (quality_checker.py:937-966): a NaN value is never
+    flagged, although the binning kernels put it in the last bin.  Thresholds come from a saved model (NaNs in the data the
+    thresholds are computed from poison them in Spark as well: unpinned)."""
+    from anovos_b200.data_analyzer import quality_checker as qc
+    rng = np.random.default_rng(2)
+    x = rng.normal(0, 1, 4000)
+    clean = pa.table({"x": pa.array(x), "y": pa.array(rng.normal(0, 1, 4000))})
+    x2 = x.copy()
+    x2[:7] = np.nan
+    x2[7:12] = 50.0
+    dirty = pa.table({"x": pa.array(x2), "y": clean.column("y")})
+    with cpu_engine.installed(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        qc.outlier_detection(None, clean, detection_side="both", treatment=False, print_impact=True, model_path=str(tmp_path))
+        base = qc.outlier_detection(None, clean, detection_side="both", pre_existing_model=True, model_path=str(tmp_path),
+                                    print_impact=True, treatment=False)[1].toPandas().set_index("attribute")
+        odf, imp = qc.outlier_detection(None, dirty, detection_side="both", pre_existing_model=True, model_path=str(tmp_path),
+                                        print_impact=True, treatment=True, treatment_method="null_replacement")
+        imp_only = qc.outlier_detection(None, dirty, detection_side="both", pre_existing_model=True, model_path=str(tmp_path),
+                                        print_impact=True, treatment=False)[1].toPandas().set_index("attribute")
+        v = odf.column("x").device()[1]
+    r = imp.toPandas().set_index("attribute")
+    clean_upper_in_first12 = int((x[:12] > 0).sum())      # at most the ordinary tail values that were overwritten
+    assert r.loc["x", "upper_outliers"] == imp_only.loc["x", "upper_outliers"]                    # rows path == histogram path
+    assert base.loc["x", "upper_outliers"] + 5 - clean_upper_in_first12 <= r.loc["x", "upper_outliers"] <= base.loc["x", "upper_outliers"] + 5
+    valid = np.unpackbits(v.numpy().view(np.uint8), bitorder="little")[:4000].astype(bool)
+    assert valid[:7].all() and not valid[7:12].any()             # NaNs stay, the five 50.0s became null
