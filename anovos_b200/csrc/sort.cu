@@ -243,82 +243,90 @@ __global__ void __launch_bounds__(ANV_BLOCK) sort_hist_kernel(const SortParams<K
   P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile] = h[tid];
 }
 
-// ---- pass step 2: per-column exclusive scan of [256][n_tiles] + skip decision ----------------------
+// ---- pass step 2: exclusive scan of [256][n_tiles] per column + skip decision ------------------------------------
+// Two launches with one CTA per (digit, column) - 256 x n_cols CTAs instead of n_cols (a batch of 15-50 columns left most of
+// the 148 SMs idle while a single CTA per column walked 6 M entries at c3):
+//   sort_totals_kernel   digit_total[c][d] = sum over tiles of tile_hist[c][d][*]
+//   sort_scan_kernel     base(d) = sum of the totals of the smaller digits (256 values, one warp scan per CTA), then the exclusive
+//                        scan of the digit's own tile counts on top of it; the CTA of digit 0 also takes the device-side
+//                        "one digit holds every key -> skip the pass" decision.
 template <typename K>
-__global__ void __launch_bounds__(1024) sort_scan_kernel(const SortParams<K> P) {
-  const int c = blockIdx.x, tid = threadIdx.x;
-  ColState& S = P.state[c];
-  __shared__ int s_skip;
-  __shared__ uint32_t wsum[2][33];   // double-buffered warp totals (+ chunk total): 2 barriers per chunk
-  if (tid == 0) s_skip = 0;
-  __syncthreads();
-  const unsigned long long n = S.n_valid;
-  uint32_t* a = P.tile_hist + (size_t)c * 256 * P.n_tiles;
-  const int64_t total = (int64_t)256 * P.n_tiles;   // a multiple of 256: every 16-entry group is whole
-  if (n > 0) {
-    constexpr int PER = 16;                           // entries per thread per chunk (4 x 128-bit)
-    const int lane = tid & 31, warp = tid >> 5;
-    uint32_t carry = 0;
-    int buf = 0;
-    for (int64_t base = 0; base < total; base += 1024 * PER, buf ^= 1) {
-      uint32_t v[PER], run = 0;
-      const int64_t i0 = base + (int64_t)tid * PER;
-      const bool in = i0 < total;
-#pragma unroll
-      for (int k = 0; k < PER / 4; ++k) {
-        const uint4 q = in ? *reinterpret_cast<const uint4*>(a + i0 + 4 * k) : make_uint4(0u, 0u, 0u, 0u);
-        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-        run += q.x + q.y + q.z + q.w;
-      }
-      uint32_t inc = run;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (lane == 31) wsum[buf][warp] = inc;
-      __syncthreads();
-      if (tid < 32) {
-        const uint32_t w = wsum[buf][tid];
-        uint32_t wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(ANV_FULL, wi, o);
-          if (tid >= o) wi += t;
-        }
-        wsum[buf][tid] = wi - w;  // exclusive
-        if (tid == 31) wsum[buf][32] = wi;
-      }
-      __syncthreads();
-      uint32_t ex = carry + wsum[buf][warp] + inc - run;
-      if (in) {
-#pragma unroll
-        for (int k = 0; k < PER / 4; ++k) {
-          uint4 q;
-          q.x = ex; ex += v[4 * k];
-          q.y = ex; ex += v[4 * k + 1];
-          q.z = ex; ex += v[4 * k + 2];
-          q.w = ex; ex += v[4 * k + 3];
-          *reinterpret_cast<uint4*>(a + i0 + 4 * k) = q;
-        }
-      }
-      carry += wsum[buf][32];
-    }
+__global__ void __launch_bounds__(ANV_BLOCK) sort_totals_kernel(const SortParams<K> P, uint32_t* __restrict__ totals) {
+  const int d = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+  const uint32_t* __restrict__ a = P.tile_hist + ((size_t)c * 256 + d) * P.n_tiles;
+  uint32_t acc = 0;
+  const int n4 = P.n_tiles & ~3;
+  if ((((size_t)c * 256 + d) * P.n_tiles & 3) == 0) {
+    for (int i = tid * 4; i < n4; i += ANV_BLOCK * 4) { const uint4 q = *reinterpret_cast<const uint4*>(a + i); acc += q.x + q.y + q.z + q.w; }
+    for (int i = n4 + tid; i < P.n_tiles; i += ANV_BLOCK) acc += a[i];
+  } else {
+    for (int i = tid; i < P.n_tiles; i += ANV_BLOCK) acc += a[i];
   }
-  __syncthreads();
-  // a digit whose total is n (its segment spans the whole prefix range) makes the pass a no-op: skip the scatter
-  if (tid < 256 && n > 0) {
-    const unsigned long long lo = a[(size_t)tid * P.n_tiles];
-    const unsigned long long hi = (tid == 255) ? n : a[(size_t)(tid + 1) * P.n_tiles];
-    if (hi - lo == n) s_skip = 1;  // (benign race: every writer writes 1)
-  }
-  if (tid == 0 && n == 0) s_skip = 1;
+  acc = __reduce_add_sync(ANV_FULL, acc);
+  __shared__ uint32_t w[ANV_WARPS];
+  if ((tid & 31) == 0) w[tid >> 5] = acc;
   __syncthreads();
   if (tid == 0) {
-    const int skip = s_skip;
+    uint32_t t = 0;
+    for (int i = 0; i < ANV_WARPS; ++i) t += w[i];
+    totals[(size_t)c * 256 + d] = t;
+  }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(ANV_BLOCK) sort_scan_kernel(const SortParams<K> P, const uint32_t* __restrict__ totals) {
+  const int d = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ColState& S = P.state[c];
+  const unsigned long long n = S.n_valid;
+  __shared__ uint32_t s_base, s_skip;
+  __shared__ uint32_t wsum[ANV_WARPS + 1];
+  if (tid == 0) s_skip = 0;
+  __syncthreads();
+  {  // base of this digit + skip decision from the 256 totals of the column (each thread owns one digit)
+    const uint32_t t = totals[(size_t)c * 256 + tid];
+    if (n > 0 && (unsigned long long)t == n) s_skip = 1;          // (benign race: every writer writes 1)
+    uint32_t below = (tid < d) ? t : 0u;
+    below = __reduce_add_sync(ANV_FULL, below);
+    if (lane == 0) wsum[warp] = below;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t b = 0;
+      for (int i = 0; i < ANV_WARPS; ++i) b += wsum[i];
+      s_base = b;
+    }
+    __syncthreads();
+  }
+  if (d == 0 && tid == 0) {
+    const int skip = (n == 0) ? 1 : (int)s_skip;
     S.src[P.pass] = S.cur;
     S.skip[P.pass] = skip;
     if (!skip) S.cur ^= 1;
+  }
+  if (n == 0) return;
+  uint32_t* a = P.tile_hist + ((size_t)c * 256 + d) * P.n_tiles;
+  uint32_t carry = s_base;
+  constexpr int PER = 8;
+  for (int base = 0; base < P.n_tiles; base += ANV_BLOCK * PER) {
+    uint32_t v[PER], run = 0;
+    const int i0 = base + tid * PER;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { v[k] = (i0 + k < P.n_tiles) ? a[i0 + k] : 0u; run += v[k]; }
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncthreads();                       // wsum of the previous chunk has been consumed
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < ANV_WARPS; ++w) { const uint32_t t = wsum[w]; woff += (w < warp) ? t : 0u; tot += t; }
+    uint32_t ex = carry + woff + inc - run;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { if (i0 + k < P.n_tiles) a[i0 + k] = ex; ex += v[k]; }
+    carry += tot;
   }
 }
 
@@ -332,8 +340,14 @@ template <typename K> struct ScatShared {   // declared ONCE in the kernel (stat
   uint16_t wcnt[SCAT_WARPS][256];             // <= 4096 keys per tile: 16 bits are enough
   uint32_t gbase[256];
   uint32_t wtot[8];
-  K sk[SORT_TILE + 1];                        // + the spare slot of the branch-free placement
+  K sk[SORT_TILE + 1];                        // + the spare slot of the branch-free placement.  During the ranking phase (before
+                                              // any key is placed) its first 16 KB serve as wmask[SCAT_WARPS][256]: per warp and
+                                              // digit, the lanes of the current round that hold the digit
 };
+
+__device__ __forceinline__ void red_shared_or(uint32_t* p, uint32_t v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 
 template <typename K, bool FULL>
 __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColState& S, const int c, const int tile, const int64_t t0,
@@ -348,10 +362,12 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
   const K* __restrict__ in = (src ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride + t0;
   K* __restrict__ out = (src ? P.buf[0] : P.buf[1]) + (size_t)c * P.stride;
   for (int i = tid; i < SCAT_WARPS * 256 / 2; i += SCAT_THREADS) reinterpret_cast<uint32_t*>(&wcnt[0][0])[i] = 0;
+  uint32_t (*wmask)[256] = reinterpret_cast<uint32_t (*)[256]>(&SH.sk[0]);
+  static_assert(sizeof(SH.sk) >= SCAT_WARPS * 256 * sizeof(uint32_t), "wmask must fit in the key staging area");
+  for (int i = tid; i < SCAT_WARPS * 256; i += SCAT_THREADS) (&wmask[0][0])[i] = 0;
   if (tid < 256) gbase[tid] = P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile];
   constexpr int WR = SORT_TILE / SCAT_WARPS / 32;  // 8 rounds per warp
   K key[WR];
-  uint32_t peers[WR];
   const int w0 = warp * (SORT_TILE / SCAT_WARPS);
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
@@ -359,26 +375,25 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
     key[r] = (FULL || i < nt) ? in[i] : (K)0;
   }
   const uint32_t lt = (1u << lane) - 1u;
+  __syncthreads();
+  // Ranking through shared memory: the lanes of a round that hold the same digit find each other by OR-ing their lane bit
+  // into the warp's word of that digit (one RED.OR + one LDS instead of 8 ballots x 5 ALU instructions); the lowest lane of
+  // each group advances the warp's digit counter and clears the word for the next round.
+  uint32_t pos[WR];
+  uint32_t okm = 0;
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
     const bool ok = FULL || (w0 + r * 32 + lane) < nt;
-    const uint32_t act = FULL ? ANV_FULL : __ballot_sync(ANV_FULL, ok);
     const uint32_t d = digit_of(key[r], P.pass);
-    const uint32_t m = peers8(d, act);
-    peers[r] = ok ? m : 0u;
-  }
-  __syncthreads();
-  uint32_t pos[WR];
-#pragma unroll
-  for (int r = 0; r < WR; ++r) {
-    const uint32_t m = peers[r];
-    const uint32_t d = digit_of(key[r], P.pass);
-    uint32_t before = 0;
-    if (m) before = wcnt[warp][d];
+    if (ok) red_shared_or(&wmask[warp][d], 1u << lane);
+    __syncwarp();
+    uint32_t m = 0, before = 0;
+    if (ok) { m = wmask[warp][d]; before = wcnt[warp][d]; }
     const uint32_t lower = m & lt;               // peers in lower lanes: none <=> this lane leads its group
     pos[r] = before + __popc(lower);
+    okm |= ok ? (1u << r) : 0u;
     __syncwarp();
-    if (m && lower == 0) wcnt[warp][d] = (uint16_t)(before + __popc(m));
+    if (ok && lower == 0) { wcnt[warp][d] = (uint16_t)(before + __popc(m)); wmask[warp][d] = 0; }
     __syncwarp();
   }
   __syncthreads();
@@ -415,7 +430,7 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
   for (int r = 0; r < WR; ++r) {   // branch-free: lanes past the end of a partial tile write to the spare slot
     const uint32_t d = digit_of(key[r], P.pass);
     const uint32_t at = wcnt[warp][d] + pos[r];
-    sk[(FULL || peers[r]) ? at : (uint32_t)SORT_TILE] = key[r];
+    sk[(FULL || ((okm >> r) & 1u)) ? at : (uint32_t)SORT_TILE] = key[r];
   }
   __syncthreads();
   if (FULL) {
@@ -627,7 +642,7 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
 }
 
 template <typename K> struct Layout {
-  size_t state, buf0, buf1, tile_hist, summ, total;
+  size_t state, buf0, buf1, tile_hist, summ, totals, total;
   Layout(int n_cols, int64_t n_rows) {
     const int64_t stride = (n_rows + 63) & ~(int64_t)63;
     const int64_t n_tiles = (n_rows + SORT_TILE - 1) / SORT_TILE;
@@ -638,6 +653,7 @@ template <typename K> struct Layout {
     buf1 = take((size_t)n_cols * stride * sizeof(K));
     tile_hist = take((size_t)n_cols * 256 * (n_tiles > 0 ? n_tiles : 1) * 4);
     summ = take((size_t)n_cols * (n_tiles > 0 ? n_tiles : 1) * sizeof(TileSummary<K>));
+    totals = take((size_t)n_cols * 256 * 4);
     total = o + 256;
   }
 };
@@ -659,6 +675,7 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   P.state = reinterpret_cast<ColState*>(w + L.state);
   P.tile_hist = reinterpret_cast<uint32_t*>(w + L.tile_hist);
   P.summ = reinterpret_cast<TileSummary<K>*>(w + L.summ);
+  uint32_t* totals = reinterpret_cast<uint32_t*>(w + L.totals);
   ANV_CUDA(cudaMemsetAsync(P.state, 0, (size_t)n_cols * sizeof(ColState), st));
   if (n_rows > 0) {
     dim3 grid(P.n_tiles, n_cols);
@@ -667,7 +684,8 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
     for (int pass = 0; pass < (int)sizeof(K); ++pass) {
       P.pass = pass;
       sort_hist_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
-      sort_scan_kernel<K><<<n_cols, 1024, 0, st>>>(P);
+      sort_totals_kernel<K><<<dim3(256, n_cols), ANV_BLOCK, 0, st>>>(P, totals);
+      sort_scan_kernel<K><<<dim3(256, n_cols), ANV_BLOCK, 0, st>>>(P, totals);
       sort_scatter_kernel<K><<<grid, SCAT_THREADS, 0, st>>>(P);
       ANV_CUDA(cudaGetLastError());
     }
@@ -1114,6 +1132,7 @@ static int run_partition_count(const anv_column_t* cols, int n_cols, int64_t n_r
   S.state = reinterpret_cast<ColState*>(ws + LS.state);
   S.tile_hist = reinterpret_cast<uint32_t*>(ws + LS.tile_hist);
   S.summ = reinterpret_cast<TileSummary<uint32_t>*>(ws + LS.summ);
+  uint32_t* totals = reinterpret_cast<uint32_t*>(ws + LS.totals);
   PcParams P{};
   P.cols = cols; P.n_cols = n_cols; P.n_rows = n_rows; P.P = L.P; P.NS = L.NS; P.NB = L.NB; P.cap = L.cap; P.m = L.m;
   P.split = reinterpret_cast<uint32_t*>(w + L.split);
@@ -1133,7 +1152,8 @@ static int run_partition_count(const anv_column_t* cols, int n_cols, int64_t n_r
     for (int pass = 0; pass < 4; ++pass) {
       S.pass = pass;
       sort_hist_kernel<uint32_t><<<tg, ANV_BLOCK, 0, st>>>(S);
-      sort_scan_kernel<uint32_t><<<n_cols, 1024, 0, st>>>(S);
+      sort_totals_kernel<uint32_t><<<dim3(256, n_cols), ANV_BLOCK, 0, st>>>(S, totals);
+      sort_scan_kernel<uint32_t><<<dim3(256, n_cols), ANV_BLOCK, 0, st>>>(S, totals);
       sort_scatter_kernel<uint32_t><<<tg, SCAT_THREADS, 0, st>>>(S);
       ANV_CUDA(cudaGetLastError());
     }

@@ -375,31 +375,33 @@ def select_ranks(frame: ColumnFrame, names, ranks):
 # ---- sort-based exact mode / distinct --------------------------------------------------------
 
 SORT_WORKSPACE_BUDGET = 24 << 30  # bytes of scratch one sort batch may use
-PARTITION_MIN_ROWS = 1 << 18      # below this the LSD sort is launch-bound anyway and needs no sampling
-sort_algorithm = "auto"           # "auto" | "lsd" | "partition" (tests force one or the other)
+sort_algorithm = "lsd"            # "lsd" | "partition" (32-bit columns through anv_mode_distinct_partition; tests run both)
 
 
-def _mode_distinct_batches(frame, idxs, names, per_col_bytes):
+def _mode_distinct_batch_size(frame, n_cols, per_col_bytes):
     torch = _lib.require_cuda()
     budget = SORT_WORKSPACE_BUDGET
-    if per_col_bytes * len(idxs) > (4 << 30):  # cudaMemGetInfo costs ~7 ms: only ask when the scratch is large
-        budget = min(budget, int(torch.cuda.mem_get_info()[0] * 0.8))
-    batch = max(1, min(len(idxs), budget // max(per_col_bytes, 1)))
-    for b0 in range(0, len(idxs), batch):
-        sub_i = idxs[b0:b0 + batch]
-        yield sub_i, [names[i] for i in sub_i]
+    if per_col_bytes * n_cols > (4 << 30):  # cudaMemGetInfo costs ~7 ms: only ask when the scratch is large, once per frame
+        key = ("sort_budget", per_col_bytes)
+        if key not in frame._cache:
+            frame._cache[key] = min(budget, int(torch.cuda.mem_get_info()[0] * 0.8))
+        budget = frame._cache[key]
+    return max(1, min(n_cols, budget // max(per_col_bytes, 1)))
 
 
 def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
     """-> list of (mode value | None, mode_rows | None, n_distinct) for NUMERIC columns.
     ranks: optional int64 [n_cols, n_ranks] of 1-based ranks among the non-null values (0 = skip);
     then returns (list, float64 [n_cols, n_ranks]) with the exact order statistics.
-    32-bit columns of >= PARTITION_MIN_ROWS rows take the partition + count path (anv_mode_distinct_partition: no
-    sort); the others - and any column that path hands back (mode_rows == -2) - the LSD radix sort."""
+    Default: the batched LSD radix sort (anv_mode_distinct).  sort_algorithm = "partition" sends 32-bit columns through
+    the partition + count path (anv_mode_distinct_partition: no sort, ~3 words of traffic per key, but its per-key global
+    atomics make it slower than the sort on B200 - DESIGN.md section 3); a column that path hands back (mode_rows == -2)
+    is redone by the sort.  All column batches of a call are enqueued back to back on the stream into one workspace (stream
+    order makes the reuse safe) and the results come back in ONE device-to-host copy."""
     if getattr(frame, "is_partitioned", False):
         return frame.sort_mode_distinct(names, ranks)
     global launch_count
-    _lib.require_cuda()
+    torch = _lib.require_cuda()
     L = _lib.lib()
     names = list(names)
     n_ranks = 0
@@ -415,46 +417,51 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
 
     def run(kb, idxs, partition):
         global launch_count
-        redo = []
-        per_col = (L.anv_mode_distinct_partition_workspace_bytes(1, frame.n_rows) if partition
-                   else L.anv_mode_distinct_workspace_bytes(1, frame.n_rows, kb))
-        for sub_i, sub in _mode_distinct_batches(frame, idxs, names, per_col):
-            desc, keep = frame.descriptors(sub)
+        n_all = len(idxs)
+        if partition:
+            ws_of = lambda n: L.anv_mode_distinct_partition_workspace_bytes(n, frame.n_rows)
+        else:
+            ws_of = lambda n: L.anv_mode_distinct_workspace_bytes(n, frame.n_rows, kb)
+        batch = _mode_distinct_batch_size(frame, n_all, ws_of(1))
+        ws_bytes = ws_of(min(batch, n_all))
+        ws = _dev_bytes(ws_bytes)
+        # one result block for the whole call: [mode_value | mode_rows | n_distinct | rank_values], 8 bytes per cell
+        out = torch.empty((3 + n_ranks) * n_all, dtype=torch.int64, device="cuda")
+        base = out.data_ptr()
+        drk = _to_dev(ranks[idxs]) if n_ranks else None
+        for b0 in range(0, n_all, batch):
+            sub = [names[i] for i in idxs[b0:b0 + batch]]
             n = len(sub)
-            ws_bytes = (L.anv_mode_distinct_partition_workspace_bytes(n, frame.n_rows) if partition
-                        else L.anv_mode_distinct_workspace_bytes(n, frame.n_rows, kb))
-            ws = _dev_bytes(ws_bytes)
-            mv, mr, nd = _dev_bytes(n * 8), _dev_bytes(n * 8), _dev_bytes(n * 8)
-            drk = _to_dev(ranks[sub_i]) if n_ranks else None
-            drv = _dev_bytes(n * n_ranks * 8) if n_ranks else None
-            common = (drk.data_ptr() if drk is not None else None, n_ranks, drv.data_ptr() if drv is not None else None,
-                      ws.data_ptr(), ws_bytes, _stream())
+            desc, keep = frame.descriptors(sub)
+            common = (drk.data_ptr() + b0 * n_ranks * 8 if n_ranks else None, n_ranks,
+                      base + (3 * n_all + b0 * n_ranks) * 8 if n_ranks else None, ws.data_ptr(), ws_bytes, _stream())
+            mv, mr, nd = base + b0 * 8, base + (n_all + b0) * 8, base + (2 * n_all + b0) * 8
             if partition:
-                _call(L.anv_mode_distinct_partition, "anv_mode_distinct_partition", desc.data_ptr(), n, frame.n_rows, mv.data_ptr(),
-                      mr.data_ptr(), nd.data_ptr(), *common, nbytes=input_bytes(frame, sub))
-                launch_count += 6 + 12
+                _call(L.anv_mode_distinct_partition, "anv_mode_distinct_partition", desc.data_ptr(), n, frame.n_rows, mv, mr, nd,
+                      *common, nbytes=input_bytes(frame, sub))
+                launch_count += 6 + 16
             else:
-                _call(L.anv_mode_distinct, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv.data_ptr(), mr.data_ptr(),
-                      nd.data_ptr(), *common, nbytes=input_bytes(frame, sub))
-                launch_count += 3 + 3 * (kb // 8)
-            hv = _host(mv).view(np.float64)[:n]
-            hr = _host(mr).view(np.int64)[:n]
-            hd = _host(nd).view(np.int64)[:n]
-            hrv = _host(drv).view(np.float64)[:n * n_ranks].reshape(n, n_ranks) if n_ranks else None
-            del ws
-            for j, (i, nme) in enumerate(zip(sub_i, sub)):
-                if hr[j] == -2:           # a bucket overflowed (sampling failure): this column goes through the sort
-                    redo.append(i)
-                    continue
-                if n_ranks:
-                    rvals[i] = hrv[j]
-                res[nme] = (float(hv[j]), int(hr[j]), int(hd[j])) if hr[j] > 0 else (None, None, 0)
+                _call(L.anv_mode_distinct, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv, mr, nd,
+                      *common, nbytes=input_bytes(frame, sub))
+                launch_count += 3 + 4 * (kb // 8)
+        host = _host(out.view(torch.uint8))
+        hv = host[:n_all * 8].view(np.float64)
+        hr = host[n_all * 8:2 * n_all * 8].view(np.int64)
+        hd = host[2 * n_all * 8:3 * n_all * 8].view(np.int64)
+        hrv = host[3 * n_all * 8:].view(np.float64).reshape(n_all, n_ranks) if n_ranks else None
+        del ws
+        redo = []
+        for j, i in enumerate(idxs):
+            if hr[j] == -2:               # a bucket overflowed (sampling failure): this column goes through the sort
+                redo.append(i)
+                continue
+            if n_ranks:
+                rvals[i] = hrv[j]
+            res[names[i]] = (float(hv[j]), int(hr[j]), int(hd[j])) if hr[j] > 0 else (None, None, 0)
         return redo
 
     for kb, idxs in groups.items():
-        use_partition = (kb == 32 and n_ranks <= 16 and sort_algorithm != "lsd"
-                         and (sort_algorithm == "partition" or frame.n_rows >= PARTITION_MIN_ROWS))
-        if use_partition:
+        if kb == 32 and n_ranks <= 16 and sort_algorithm == "partition":
             idxs = run(kb, idxs, True)
         if idxs:
             run(kb, idxs, False)

@@ -299,6 +299,12 @@ def _run_ours(args, out):
                    "share_of_step": v["ms"] / ms} for k, v in sorted(kt.items())}
     kernel_ms = sum(v["ms"] for v in kt.values()) / args.steps
 
+    rowslab = None
+    if world > 1 and not args.no_extras:      # every rank takes part (collectives), outside the timed region
+        try:
+            rowslab = rowslab_check(rank, world, torch, dist)
+        except Exception as ex:
+            rowslab = {"error": repr(ex)}
     line = None
     if rank == 0:
         extra, e2e, cpu, parity = {}, None, None, None
@@ -342,12 +348,72 @@ def _run_ours(args, out):
                            "kernel_ms_per_step": kernel_ms, "host_ms_per_step": ms_per_step - kernel_ms},
                 "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roofline,
                 "roofline_kernels": roofline_kernels, "cpu_baseline": cpu, "parity": parity, "kernels": kernels,
-                "fused_stats_hist_pass": extra}
+                "fused_stats_hist_pass": extra, "rowslab_nccl": rowslab}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         out.emit(json.dumps(line))
+
+
+def rowslab_check(rank, world, torch, dist):
+    """N >= 2 only, outside the timed region, EVERY rank: the row-sharded variant of the path under NCCL.  Each
+    rank holds a row slab of all columns of one frame; moments / histograms / HLL registers / radix-select histograms merge with
+    all_gather + all_reduce, the exact mode needs the one real exchange of the path (row slabs -> column blocks, grouped
+    point-to-point sends over NVLink).  Results must equal the single-frame results computed locally on every rank."""
+    import tempfile
+    import numpy as np
+    import anovos.data_analyzer.stats_generator as sg
+    import anovos.drift_stability.drift_detector as dd
+    from anovos_b200 import engine, parallel, synth
+    from anovos_b200.partitioned import PartitionedFrame, repartition_to_columns
+    ROWS, COLS = 4_000_000, 16
+    per = ROWS // world // 32 * 32
+    r0 = rank * per
+    r1 = ROWS if rank == world - 1 else r0 + per
+
+    def mk(seed, a=0, b=ROWS):
+        return synth.device_frame(b - a, COLS, seed=seed, cat_every=4, row0=a, shifted=seed != 42)
+    whole, twhole = mk(42), mk(43)
+    slab, tslab = mk(42, r0, r1), mk(43, r0, r1)
+    parts = PartitionedFrame.from_frame(slab, 1 << 19, group=True)
+    tparts = PartitionedFrame.from_frame(tslab, 1 << 19, group=True)
+    ok = parts.count() == ROWS
+    mw, mp = engine.moments(whole, whole.columns), engine.moments(parts, whole.columns)
+    ok &= all(np.array_equal(mw[f], mp[f], equal_nan=True) for f in ("n_valid", "n_nonzero", "min", "max"))
+    ok &= all(np.allclose(mw[f], mp[f], rtol=1e-9, atol=0) for f in ("mean", "m2", "m4"))
+    for fn in ("measures_of_counts", "measures_of_percentiles", "measures_of_cardinality", "measures_of_centralTendency"):
+        ok &= getattr(sg, fn)(None, whole).toPandas().equals(getattr(sg, fn)(None, parts).toPandas())
+    kw = dict(method_type="all", use_sampling=False)
+    a = dd.statistics(None, twhole, whole, source_path=tempfile.mkdtemp(), **kw).toPandas()
+    b = dd.statistics(None, tparts, parts, source_path=tempfile.mkdtemp(), **kw).toPandas()
+    ok &= all(np.allclose(a[m], b[m], rtol=1e-9, atol=0) for m in ("PSI", "HD", "JSD", "KS")) and list(a["flagged"]) == list(b["flagged"])
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mine = repartition_to_columns(slab, True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    names = parallel.shard_columns(slab.columns, rank, world)
+    ok &= mine.columns == names and mine.count() == ROWS
+    for n in names:
+        d, v = mine.column(n).device()
+        dw, vw = whole.column(n).device()
+        ok &= bool(torch.equal(d, dw)) and ((v is None and vw is None) or bool(torch.equal(v.view(torch.int32), vw.view(torch.int32))))
+    t = torch.tensor([1.0 if ok else 0.0, ms], dtype=torch.float64, device="cuda")
+    tmin = t.clone()
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    recv_bytes = sum(ROWS * 4 for _ in names) * (world - 1) / world
+    return {"ok_on_every_rank": bool(tmin[0].item() == 1.0), "ranks": world, "rows": ROWS, "cols": COLS,
+            "checked": "row-slab moments / counts / percentiles / HLL / exact mode / drift == single-frame results; "
+                       "repartition_to_columns == the whole columns bit for bit",
+            "exchange_ms_max_over_ranks": float(t[1].item()),
+            "exchange_gbs_per_rank": recv_bytes / (float(t[1].item()) * 1e-3) / 1e9,
+            "collectives": "all_gather(moment records) + all_reduce(sum: histograms, code counts, select histograms; max: HLL registers) "
+                           "+ batched isend/irecv (row slabs -> column blocks) over NCCL"}
 
 
 def parity_check(rows, cols, first_col, cat_every, src, frames, drift_res):

@@ -357,7 +357,9 @@ def test_partition_count_adversarial_columns(n):
         ref, qr = engine.sort_mode_distinct(fr, names, rk)
     finally:
         engine.sort_algorithm = old
-    assert got == ref
+    def same(a, b):      # (mode, rows, distinct) tuples; the mode of a NaN-dominated column is NaN on both sides
+        return a == b or (a[1:] == b[1:] and a[0] != a[0] and b[0] != b[0])
+    assert all(same(a, b) for a, b in zip(got, ref)), [(n, a, b) for n, a, b in zip(names, got, ref) if not same(a, b)]
     assert np.array_equal(qv, qr, equal_nan=True)
     for i, c in enumerate(names):
         vals, valid = S.column_values(t, c)
