@@ -18,6 +18,8 @@
 //            the merge kernel splices the zero run back and reads the requested order statistics.
 // Counting is integer everywhere => deterministic.  Ties for the mode resolve to the
 // smallest value (the reference's choice is arbitrary, stats_generator.py:358).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace anv {
@@ -66,6 +68,7 @@ struct ColState {               // one per column, in the workspace
   int cur;                      // which ping-pong buffer holds the current order
   int src[8];                   // per pass: source buffer
   int skip[8];                  // per pass: digit constant -> no scatter
+  int error;                    // look-back spin limit hit (never expected): the host raises instead of hanging
 };
 
 template <typename K> struct TileSummary {
@@ -84,7 +87,17 @@ template <typename K> struct SortParams {
   uint32_t* tile_hist;          // [n_cols][256][n_tiles]  (digit-major)
   TileSummary<K>* summ;         // [n_cols][n_tiles]
   int pass;
+  // one-sweep passes (decoupled look-back): no tile-histogram and no scan kernel
+  uint32_t* ghist;              // [n_cols][sizeof(K)][256]  digit counts of the whole column, all passes, taken by pack_kernel
+  uint32_t* gbase;              // [n_cols][sizeof(K)][256]  their exclusive scans
+  unsigned long long* status;   // [n_cols][n_tiles][256]   (epoch << 56 | kind << 54 | count): tile aggregates / inclusive prefixes
+  uint32_t* ticket;             // [n_cols][sizeof(K)]       tile ids are handed out in arrival order
 };
+constexpr int PACK_TPC = 8;     // tiles per pack CTA (amortises the flush of the digit histograms)
+
+template <typename K> __device__ __forceinline__ uint32_t digit_of(K k, int pass) {
+  return (uint32_t)(k >> (pass * 8)) & 0xFFu;
+}
 
 // ---- pack: values -> keys, nulls dropped --------------------------------------------------
 // One CTA per 4096-row tile: 128-bit loads, block-level compaction (one atomicAdd per CTA
@@ -93,12 +106,12 @@ template <typename K> struct SortParams {
 // benchmark's fourth family, > 90 % in the income dataset's capital-gain / capital-loss) then sort only their
 // nonzero values; run_merge_kernel splices the zero run back into mode, distinct count and ranks.
 template <typename K, typename T>
-__device__ __forceinline__ void pack_tile(const SortParams<K>& P, const anv_column_t& col, int c, uint32_t* s_warp,
-                                          unsigned long long* s_base, K* sk) {
+__device__ __forceinline__ void pack_tile(const SortParams<K>& P, const anv_column_t& col, int c, const int64_t tile, uint32_t* s_warp,
+                                          unsigned long long* s_base, K* sk, uint32_t (*s_dh)[256]) {
   constexpr int VEC = Traits<T>::VEC;
   constexpr int PER = SORT_TILE / ANV_BLOCK;  // 16 rows per thread, contiguous
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * SORT_TILE;
+  const int64_t r0 = tile * SORT_TILE;
   const int n_tile = (int)min((int64_t)SORT_TILE, P.n_rows - r0);
   const T* __restrict__ data = reinterpret_cast<const T*>(col.data) + r0;
   const uint32_t* __restrict__ vbits = col.validity;
@@ -170,7 +183,15 @@ __device__ __forceinline__ void pack_tile(const SortParams<K>& P, const anv_colu
   __syncthreads();
   K* __restrict__ out = P.buf[0] + (size_t)c * P.stride + *s_base;
   const uint32_t total = s_total;
-  for (uint32_t i = tid; i < total; i += ANV_BLOCK) out[i] = sk[i];
+  // copy-out + the digit histograms of EVERY pass from the staged keys (the one-sweep passes need the column-wide digit counts
+  // before the first scatter; taking them here replaces one full read of the keys per pass)
+  for (uint32_t i = tid; i < total; i += ANV_BLOCK) {
+    const K k = sk[i];
+    out[i] = k;
+#pragma unroll
+    for (int ps = 0; ps < (int)sizeof(K); ++ps) atomicAdd(&s_dh[ps][digit_of(k, ps)], 1u);
+  }
+  __syncthreads();   // sk / s_warp are reused by the CTA's next tile
 }
 
 template <typename K>
@@ -178,14 +199,65 @@ __global__ void __launch_bounds__(ANV_BLOCK) pack_kernel(const SortParams<K> P) 
   __shared__ uint32_t s_warp[ANV_WARPS];
   __shared__ unsigned long long s_base;
   __shared__ K sk[SORT_TILE];
-  const int c = blockIdx.y;
+  __shared__ uint32_t s_dh[sizeof(K)][256];
+  const int c = blockIdx.y, tid = threadIdx.x;
   const anv_column_t col = P.cols[c];
-  switch (col.dtype) {
-    case ANV_F32: pack_tile<K, float>(P, col, c, s_warp, &s_base, sk); break;
-    case ANV_I32: pack_tile<K, int32_t>(P, col, c, s_warp, &s_base, sk); break;
-    case ANV_F64: if (sizeof(K) == 8) pack_tile<K, double>(P, col, c, s_warp, &s_base, sk); break;
-    case ANV_I64: if (sizeof(K) == 8) pack_tile<K, int64_t>(P, col, c, s_warp, &s_base, sk); break;
-    default: break;
+#pragma unroll
+  for (int ps = 0; ps < (int)sizeof(K); ++ps) s_dh[ps][tid] = 0;
+  __syncthreads();
+  for (int t = 0; t < PACK_TPC; ++t) {
+    const int64_t tile = (int64_t)blockIdx.x * PACK_TPC + t;
+    if (tile * SORT_TILE >= P.n_rows) break;
+    switch (col.dtype) {
+      case ANV_F32: pack_tile<K, float>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
+      case ANV_I32: pack_tile<K, int32_t>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
+      case ANV_F64: if (sizeof(K) == 8) pack_tile<K, double>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
+      case ANV_I64: if (sizeof(K) == 8) pack_tile<K, int64_t>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
+      default: break;
+    }
+  }
+  __syncthreads();
+  uint32_t* g = P.ghist + (size_t)c * sizeof(K) * 256;
+#pragma unroll
+  for (int ps = 0; ps < (int)sizeof(K); ++ps) {
+    const uint32_t v = s_dh[ps][tid];
+    if (v) atomicAdd(&g[ps * 256 + tid], v);
+  }
+}
+
+// Column-wide exclusive digit offsets of every pass + which passes are no-ops (one digit holds every key) + the ping-pong
+// buffer each pass reads: everything the one-sweep passes need is known after the pack kernel.
+template <typename K>
+__global__ void __launch_bounds__(ANV_BLOCK) sort_bases_kernel(const SortParams<K> P) {
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ColState& S = P.state[c];
+  const unsigned long long n = S.n_valid;
+  __shared__ uint32_t wsum[ANV_WARPS];
+  __shared__ int s_skip[sizeof(K)];
+  if (tid < (int)sizeof(K)) s_skip[tid] = (n == 0) ? 1 : 0;
+  __syncthreads();
+  for (int ps = 0; ps < (int)sizeof(K); ++ps) {
+    const uint32_t v = P.ghist[((size_t)c * sizeof(K) + ps) * 256 + tid];
+    if (n > 0 && (unsigned long long)v == n) s_skip[ps] = 1;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < ANV_WARPS; ++w) woff += (w < warp) ? wsum[w] : 0u;
+    P.gbase[((size_t)c * sizeof(K) + ps) * 256 + tid] = woff + inc - v;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int cur = 0;
+    for (int ps = 0; ps < (int)sizeof(K); ++ps) {
+      S.src[ps] = cur;
+      S.skip[ps] = s_skip[ps];
+      if (!s_skip[ps]) cur ^= 1;
+    }
+    S.cur = cur;
   }
 }
 
@@ -204,9 +276,6 @@ __device__ __forceinline__ uint32_t peers8(uint32_t d, uint32_t act) {
 }
 #undef ANV_PEER_BIT
 
-template <typename K> __device__ __forceinline__ uint32_t digit_of(K k, int pass) {
-  return (uint32_t)(k >> (pass * 8)) & 0xFFu;
-}
 
 // ---- pass step 1: per-tile digit histogram ------------------------------------------------------
 // Plain shared-memory atomics (hardware handles same-address lanes far faster than a
@@ -340,16 +409,32 @@ template <typename K> struct ScatShared {   // declared ONCE in the kernel (stat
   uint16_t wcnt[SCAT_WARPS][256];             // <= 4096 keys per tile: 16 bits are enough
   uint32_t gbase[256];
   uint32_t wtot[8];
-  K sk[SORT_TILE + 1];                        // + the spare slot of the branch-free placement.  During the ranking phase (before
-                                              // any key is placed) its first 16 KB serve as wmask[SCAT_WARPS][256]: per warp and
-                                              // digit, the lanes of the current round that hold the digit
+  K sk[SORT_TILE + 1];                        // + the spare slot of the branch-free placement
 };
 
-__device__ __forceinline__ void red_shared_or(uint32_t* p, uint32_t v) {
-  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+constexpr unsigned long long LB_AGG = 1ull << 54, LB_PREFIX = 2ull << 54, LB_VALUE = (1ull << 54) - 1ull;
+constexpr int LB_SPIN_LIMIT = 1 << 22;
+
+// Decoupled look-back of ONE digit: add up the aggregates of the preceding tiles until one that already knows its inclusive
+// prefix, then publish this tile's inclusive prefix.  (Not inlined: keeps the spin loop out of the scatter's control flow.)
+__device__ __noinline__ unsigned long long lookback_exclusive(volatile unsigned long long* status, int tile, int d, unsigned long long epoch,
+                                                             unsigned long long total, int* error) {
+  unsigned long long excl = 0;
+  for (int t = tile - 1; t >= 0; --t) {
+    unsigned long long v = status[(size_t)t * 256 + d];
+    int spins = 0;
+    while ((v >> 56) != (epoch >> 56)) {
+      if (++spins > LB_SPIN_LIMIT) { *error = 1; return excl; }     // never expected: tiles start in ticket order
+      v = status[(size_t)t * 256 + d];
+    }
+    excl += v & LB_VALUE;
+    if (v & LB_PREFIX) break;
+  }
+  status[(size_t)tile * 256 + d] = epoch | LB_PREFIX | (excl + total);
+  return excl;
 }
 
-template <typename K, bool FULL>
+template <typename K, bool FULL, bool LOOKBACK>
 __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColState& S, const int c, const int tile, const int64_t t0,
                                              const int nt_in, ScatShared<K>& SH) {
   auto& wcnt = SH.wcnt;
@@ -362,12 +447,10 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
   const K* __restrict__ in = (src ? P.buf[1] : P.buf[0]) + (size_t)c * P.stride + t0;
   K* __restrict__ out = (src ? P.buf[0] : P.buf[1]) + (size_t)c * P.stride;
   for (int i = tid; i < SCAT_WARPS * 256 / 2; i += SCAT_THREADS) reinterpret_cast<uint32_t*>(&wcnt[0][0])[i] = 0;
-  uint32_t (*wmask)[256] = reinterpret_cast<uint32_t (*)[256]>(&SH.sk[0]);
-  static_assert(sizeof(SH.sk) >= SCAT_WARPS * 256 * sizeof(uint32_t), "wmask must fit in the key staging area");
-  for (int i = tid; i < SCAT_WARPS * 256; i += SCAT_THREADS) (&wmask[0][0])[i] = 0;
-  if (tid < 256) gbase[tid] = P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile];
+  if (!LOOKBACK && tid < 256) gbase[tid] = P.tile_hist[((size_t)c * 256 + tid) * P.n_tiles + tile];
   constexpr int WR = SORT_TILE / SCAT_WARPS / 32;  // 8 rounds per warp
   K key[WR];
+  uint32_t peers[WR];
   const int w0 = warp * (SORT_TILE / SCAT_WARPS);
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
@@ -375,25 +458,26 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
     key[r] = (FULL || i < nt) ? in[i] : (K)0;
   }
   const uint32_t lt = (1u << lane) - 1u;
-  __syncthreads();
-  // Ranking through shared memory: the lanes of a round that hold the same digit find each other by OR-ing their lane bit
-  // into the warp's word of that digit (one RED.OR + one LDS instead of 8 ballots x 5 ALU instructions); the lowest lane of
-  // each group advances the warp's digit counter and clears the word for the next round.
-  uint32_t pos[WR];
-  uint32_t okm = 0;
 #pragma unroll
   for (int r = 0; r < WR; ++r) {
     const bool ok = FULL || (w0 + r * 32 + lane) < nt;
+    const uint32_t act = FULL ? ANV_FULL : __ballot_sync(ANV_FULL, ok);
     const uint32_t d = digit_of(key[r], P.pass);
-    if (ok) red_shared_or(&wmask[warp][d], 1u << lane);
-    __syncwarp();
-    uint32_t m = 0, before = 0;
-    if (ok) { m = wmask[warp][d]; before = wcnt[warp][d]; }
+    const uint32_t m = peers8(d, act);
+    peers[r] = ok ? m : 0u;
+  }
+  __syncthreads();
+  uint32_t pos[WR];
+#pragma unroll
+  for (int r = 0; r < WR; ++r) {
+    const uint32_t m = peers[r];
+    const uint32_t d = digit_of(key[r], P.pass);
+    uint32_t before = 0;
+    if (m) before = wcnt[warp][d];
     const uint32_t lower = m & lt;               // peers in lower lanes: none <=> this lane leads its group
     pos[r] = before + __popc(lower);
-    okm |= ok ? (1u << r) : 0u;
     __syncwarp();
-    if (ok && lower == 0) { wcnt[warp][d] = (uint16_t)(before + __popc(m)); wmask[warp][d] = 0; }
+    if (m && lower == 0) wcnt[warp][d] = (uint16_t)(before + __popc(m));
     __syncwarp();
   }
   __syncthreads();
@@ -404,6 +488,11 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
     for (int w = 0; w < SCAT_WARPS; ++w) { const uint32_t t = wcnt[w][tid]; wcnt[w][tid] = (uint16_t)acc; acc += t; }
     total = acc;
   }
+  const unsigned long long epoch = (unsigned long long)(P.pass + 1) << 56;
+  volatile unsigned long long* const status = LOOKBACK ? P.status + ((size_t)c * P.n_tiles) * 256 : nullptr;
+  if (LOOKBACK && tid < 256)   // publish this tile's digit counts at once: its successors only need these to move on
+    status[(size_t)tile * 256 + tid] = epoch | (tile == 0 ? LB_PREFIX : LB_AGG) | (unsigned long long)total;
+  uint32_t ds_keep = 0;
   {  // exclusive scan of the 256 digit totals -> start of each digit inside the reordered tile
     uint32_t inc = total;
 #pragma unroll
@@ -422,7 +511,8 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
       // "global base minus tile start" table for the copy-out (one lookup per key there as well)
 #pragma unroll
       for (int w = 0; w < SCAT_WARPS; ++w) wcnt[w][tid] = (uint16_t)(wcnt[w][tid] + ds);
-      gbase[tid] -= ds;
+      if (LOOKBACK) ds_keep = ds;
+      else gbase[tid] -= ds;
     }
   }
   __syncthreads();
@@ -430,7 +520,11 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
   for (int r = 0; r < WR; ++r) {   // branch-free: lanes past the end of a partial tile write to the spare slot
     const uint32_t d = digit_of(key[r], P.pass);
     const uint32_t at = wcnt[warp][d] + pos[r];
-    sk[(FULL || ((okm >> r) & 1u)) ? at : (uint32_t)SORT_TILE] = key[r];
+    sk[(FULL || peers[r]) ? at : (uint32_t)SORT_TILE] = key[r];
+  }
+  if (LOOKBACK && tid < 256) {
+    const unsigned long long excl = lookback_exclusive(status, tile, tid, epoch, (unsigned long long)total, &P.state[c].error);
+    gbase[tid] = P.gbase[((size_t)c * sizeof(K) + P.pass) * 256 + tid] + (uint32_t)excl - ds_keep;
   }
   __syncthreads();
   if (FULL) {
@@ -458,8 +552,30 @@ __global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const Sor
   if (t0 >= n) return;
   const int nt = (int)min((int64_t)SORT_TILE, n - t0);
   __shared__ ScatShared<K> SH;
-  if (nt == SORT_TILE) scatter_tile<K, true>(P, S, c, tile, t0, nt, SH);
-  else scatter_tile<K, false>(P, S, c, tile, t0, nt, SH);
+  if (nt == SORT_TILE) scatter_tile<K, true, false>(P, S, c, tile, t0, nt, SH);
+  else scatter_tile<K, false, false>(P, S, c, tile, t0, nt, SH);
+}
+
+// One-sweep pass: the same stable scatter, but the tile's global digit offsets come from the column-wide digit bases
+// (sort_bases_kernel) + a decoupled look-back over the preceding tiles' digit counts - one read and one write of the keys per
+// pass, no tile-histogram kernel, no scan kernel.  Tile ids are tickets (arrival order), so every tile a CTA waits for has
+// already started: the look-back cannot deadlock.
+template <typename K>
+__global__ void __launch_bounds__(SCAT_THREADS, 2) sort_onesweep_kernel(const SortParams<K> P) {
+  const int c = blockIdx.y;
+  const ColState& S = P.state[c];
+  if (S.skip[P.pass]) return;
+  __shared__ int s_tile;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&P.ticket[(size_t)c * sizeof(K) + P.pass], 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t n = (int64_t)S.n_valid;
+  const int64_t t0 = (int64_t)tile * SORT_TILE;
+  if (t0 >= n) return;
+  const int nt = (int)min((int64_t)SORT_TILE, n - t0);
+  __shared__ ScatShared<K> SH;
+  if (nt == SORT_TILE) scatter_tile<K, true, true>(P, S, c, tile, t0, nt, SH);
+  else scatter_tile<K, false, true>(P, S, c, tile, t0, nt, SH);
 }
 
 // Associative combine of two ADJACENT run summaries (left, right) of sorted keys.
@@ -605,6 +721,10 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
     }
     rank_values[(size_t)c * n_ranks + r] = v;
   }
+  if (S.error) {                      // a look-back gave up: make the host raise (results would be garbage)
+    if (lane == 0) { mode_value[c] = nan(""); mode_rows[c] = -3; n_distinct[c] = -3; }
+    return;
+  }
   if (n == 0) {
     if (lane == 0) {
       mode_value[c] = nz ? sorted_key_to_double(sizeof(K) == 8 ? (uint64_t)ZERO_KEY : ((uint64_t)ZERO_KEY << 32), dt) : nan("");
@@ -642,7 +762,7 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
 }
 
 template <typename K> struct Layout {
-  size_t state, buf0, buf1, tile_hist, summ, totals, total;
+  size_t state, buf0, buf1, tile_hist, summ, totals, ghist, gbase, ticket, status, total;
   Layout(int n_cols, int64_t n_rows) {
     const int64_t stride = (n_rows + 63) & ~(int64_t)63;
     const int64_t n_tiles = (n_rows + SORT_TILE - 1) / SORT_TILE;
@@ -654,6 +774,10 @@ template <typename K> struct Layout {
     tile_hist = take((size_t)n_cols * 256 * (n_tiles > 0 ? n_tiles : 1) * 4);
     summ = take((size_t)n_cols * (n_tiles > 0 ? n_tiles : 1) * sizeof(TileSummary<K>));
     totals = take((size_t)n_cols * 256 * 4);
+    ghist = take((size_t)n_cols * sizeof(K) * 256 * 4);     // ghist, gbase, ticket, status are contiguous: one memset
+    gbase = take((size_t)n_cols * sizeof(K) * 256 * 4);
+    ticket = take((size_t)n_cols * sizeof(K) * 4);
+    status = take((size_t)n_cols * (n_tiles > 0 ? n_tiles : 1) * 256 * 8);
     total = o + 256;
   }
 };
@@ -676,18 +800,38 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   P.tile_hist = reinterpret_cast<uint32_t*>(w + L.tile_hist);
   P.summ = reinterpret_cast<TileSummary<K>*>(w + L.summ);
   uint32_t* totals = reinterpret_cast<uint32_t*>(w + L.totals);
+  P.ghist = reinterpret_cast<uint32_t*>(w + L.ghist);
+  P.gbase = reinterpret_cast<uint32_t*>(w + L.gbase);
+  P.ticket = reinterpret_cast<uint32_t*>(w + L.ticket);
+  P.status = reinterpret_cast<unsigned long long*>(w + L.status);
+  static const bool legacy_env = getenv("ANV_SORT_LEGACY") != nullptr;   // force the three-kernel passes (tile histogram, scan, scatter)
+  const bool legacy = legacy_env || sizeof(K) != 4;
   ANV_CUDA(cudaMemsetAsync(P.state, 0, (size_t)n_cols * sizeof(ColState), st));
+  ANV_CUDA(cudaMemsetAsync(w + L.ghist, 0, legacy ? L.status - L.ghist : L.total - 256 - L.ghist, st));
   if (n_rows > 0) {
     dim3 grid(P.n_tiles, n_cols);
-    pack_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
+    pack_kernel<K><<<dim3((P.n_tiles + PACK_TPC - 1) / PACK_TPC, n_cols), ANV_BLOCK, 0, st>>>(P);
     ANV_CUDA(cudaGetLastError());
-    for (int pass = 0; pass < (int)sizeof(K); ++pass) {
-      P.pass = pass;
-      sort_hist_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
-      sort_totals_kernel<K><<<dim3(256, n_cols), ANV_BLOCK, 0, st>>>(P, totals);
-      sort_scan_kernel<K><<<dim3(256, n_cols), ANV_BLOCK, 0, st>>>(P, totals);
-      sort_scatter_kernel<K><<<grid, SCAT_THREADS, 0, st>>>(P);
-      ANV_CUDA(cudaGetLastError());
+    // 64-bit keys keep the three-kernel passes: ptxas (12.9) does not terminate on the uint64 instantiation of the one-sweep kernel
+    if constexpr (sizeof(K) == 4) {
+      if (!legacy) {
+        sort_bases_kernel<K><<<n_cols, ANV_BLOCK, 0, st>>>(P);
+        for (int pass = 0; pass < (int)sizeof(K); ++pass) {
+          P.pass = pass;
+          sort_onesweep_kernel<K><<<grid, SCAT_THREADS, 0, st>>>(P);
+          ANV_CUDA(cudaGetLastError());
+        }
+      }
+    }
+    if (legacy || sizeof(K) != 4) {
+      for (int pass = 0; pass < (int)sizeof(K); ++pass) {
+        P.pass = pass;
+        sort_hist_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
+        sort_totals_kernel<K><<<dim3(256, n_cols), ANV_BLOCK, 0, st>>>(P, totals);
+        sort_scan_kernel<K><<<dim3(256, n_cols), ANV_BLOCK, 0, st>>>(P, totals);
+        sort_scatter_kernel<K><<<grid, SCAT_THREADS, 0, st>>>(P);
+        ANV_CUDA(cudaGetLastError());
+      }
     }
     run_tile_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
     ANV_CUDA(cudaGetLastError());

@@ -452,6 +452,9 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
         del ws
         redo = []
         for j, i in enumerate(idxs):
+            if hr[j] == -3:
+                raise _lib.AnvError("anv_mode_distinct: a one-sweep look-back gave up waiting for a preceding tile (column %r); "
+                                    "set ANV_SORT_LEGACY=1 to use the three-kernel passes" % names[i])
             if hr[j] == -2:               # a bucket overflowed (sampling failure): this column goes through the sort
                 redo.append(i)
                 continue
@@ -512,6 +515,40 @@ def hll_estimates_from_register_rows(R: np.ndarray, p: int):
     return out
 
 
+_DICT_HLL = {}   # (id(dictionary), p) -> (dictionary, register index per entry, rho per entry)
+
+
+def _dictionary_hll(dic, p: int):
+    """HLL++ (register index, rho) of every entry of a string dictionary: Spark's XXH64 (seed 42) over the UTF-8 bytes
+    (anv_xxh64_utf8, host helper of the library), idx = top p bits, rho = clz(rest) + 1.  Cached per dictionary object."""
+    key = (id(dic), p)
+    hit = _DICT_HLL.get(key)
+    if hit is not None and hit[0] is dic:
+        return hit[1], hit[2]
+    L = _lib.lib()
+    enc = [s.encode("utf-8") for s in dic]
+    hs = np.zeros(len(enc), np.uint64)
+    if enc:
+        offs = np.zeros(len(enc) + 1, np.int64)
+        np.cumsum([len(b) for b in enc], out=offs[1:])
+        blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+        _lib.check(L.anv_xxh64_utf8(blob.ctypes.data, offs.ctypes.data, len(enc), hs.ctypes.data), "anv_xxh64_utf8")
+    idx = (hs >> np.uint64(64 - p)).astype(np.int64)
+    w = (hs << np.uint64(p)) | np.uint64(1 << (p - 1))
+    # clz64(w) + 1 without a Python loop: position of the highest set bit from the float64 exponent is unsafe for 64-bit
+    # values, so split into halves (each < 2^32 is exact in float64)
+    hi, lo = (w >> np.uint64(32)).astype(np.float64), (w & np.uint64(0xFFFFFFFF)).astype(np.float64)
+    with np.errstate(divide="ignore"):
+        bl_hi = np.where(hi > 0, np.floor(np.log2(np.maximum(hi, 1))) + 33, 0)
+        bl_lo = np.where(lo > 0, np.floor(np.log2(np.maximum(lo, 1))) + 1, 0)
+    bitlen = np.where(hi > 0, bl_hi, bl_lo).astype(np.int64)
+    rho = (64 - bitlen + 1).astype(np.uint32)
+    if len(_DICT_HLL) > 256:
+        _DICT_HLL.clear()
+    _DICT_HLL[key] = (dic, idx, rho)
+    return idx, rho
+
+
 def hll_registers(frame: ColumnFrame, names, p: int):
     """-> uint32 [n_cols, 2**p] HLL++ registers of NUMERIC columns (max-mergeable across row partitions)."""
     if getattr(frame, "is_partitioned", False):
@@ -543,24 +580,14 @@ def hll_estimates(frame: ColumnFrame, names, p: int):
         for n, r in zip(num, hll_estimates_from_register_rows(R, p)):
             out[n] = r
     if cat:
-        # per-row work (the code histogram) runs on the device; only the dictionary entries that
-        # actually occur are hashed on the host, once each
+        # per-row work (the code histogram) runs on the device; every dictionary entry is hashed on the host ONCE per
+        # dictionary (cached: register index and rho of each entry), so a step only takes a masked maximum
         cc = code_counts(frame, cat)
         for n, h in zip(cat, cc):
-            dic = frame.column(n).dictionary
-            present = [dic[i].encode("utf-8") for i in np.flatnonzero(h[1:])]
+            idx, rho = _dictionary_hll(frame.column(n).dictionary, p)
             regs = np.zeros(m, np.uint32)
-            if present:
-                offs = np.zeros(len(present) + 1, np.int64)
-                np.cumsum([len(b) for b in present], out=offs[1:])
-                blob = np.frombuffer(b"".join(present) or b"\0", dtype=np.uint8)
-                hs = np.zeros(len(present), np.uint64)
-                _call(L.anv_xxh64_utf8, "anv_xxh64_utf8", blob.ctypes.data, offs.ctypes.data, len(present), hs.ctypes.data)
-                idx = (hs >> np.uint64(64 - p)).astype(np.int64)
-                w = (hs << np.uint64(p)) | np.uint64(1 << (p - 1))
-                rho = np.zeros(len(hs), np.uint32)
-                for i, x in enumerate(w.tolist()):
-                    rho[i] = 64 - x.bit_length() + 1
-                np.maximum.at(regs, idx, rho)
+            present = np.flatnonzero(h[1:])
+            if present.size:
+                np.maximum.at(regs, idx[present], rho[present])
             out[n] = hll_estimate_from_registers(regs, p)
     return [out[n] for n in names]
