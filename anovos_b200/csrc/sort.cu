@@ -413,7 +413,7 @@ template <typename K> struct ScatShared {   // declared ONCE in the kernel (stat
 };
 
 constexpr unsigned long long LB_AGG = 1ull << 54, LB_PREFIX = 2ull << 54, LB_VALUE = (1ull << 54) - 1ull;
-constexpr int LB_SPIN_LIMIT = 1 << 22;
+constexpr int LB_SPIN_LIMIT = 1 << 20;
 
 // Decoupled look-back of ONE digit: add up the aggregates of the preceding tiles until one that already knows its inclusive
 // prefix, then publish this tile's inclusive prefix.  (Not inlined: keeps the spin loop out of the scatter's control flow.)
@@ -424,7 +424,8 @@ __device__ __noinline__ unsigned long long lookback_exclusive(volatile unsigned 
     unsigned long long v = status[(size_t)t * 256 + d];
     int spins = 0;
     while ((v >> 56) != (epoch >> 56)) {
-      if (++spins > LB_SPIN_LIMIT) { *error = 1; return excl; }     // never expected: tiles start in ticket order
+      // never expected (tiles start in ticket order); once one look-back has given up every other one follows at once
+      if (++spins > LB_SPIN_LIMIT || ((spins & 255) == 0 && *reinterpret_cast<volatile int*>(error))) { *error = 1; return excl; }
       v = status[(size_t)t * 256 + d];
     }
     excl += v & LB_VALUE;
