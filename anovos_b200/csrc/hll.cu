@@ -55,7 +55,9 @@ struct HllParams {
   int use_smem;
 };
 
-template <typename T, bool NULLS>
+// SMEM: registers of the tile live in shared memory (p <= 14) - a compile-time fact, so the register update is an LDS +
+// (rarely) an ATOMS.MAX instead of generic-address loads and atomics.
+template <typename T, bool NULLS, bool SMEM>
 __device__ __forceinline__ void hll_tile(const HllParams& P, const anv_column_t& col, int c, uint32_t* sh) {
   constexpr int VEC = Traits<T>::VEC;
   constexpr uint32_t VMASK = (1u << VEC) - 1u;
@@ -65,19 +67,25 @@ __device__ __forceinline__ void hll_tile(const HllParams& P, const anv_column_t&
   const int64_t r1 = min(r0 + (int64_t)P.tile_rows, P.n_rows);
   const T* __restrict__ data = reinterpret_cast<const T*>(col.data);
   const uint32_t* __restrict__ vbits = col.validity;
-  uint32_t* R = P.use_smem ? sh : P.regs + (size_t)c * m;
-  if (P.use_smem) {
+  uint32_t* const G = P.regs + (size_t)c * m;
+  if (SMEM) {
     for (int i = tid; i < m; i += ANV_BLOCK) sh[i] = 0;
     __syncthreads();
   }
   const int p = P.p;
+  const int ps = 64 - p;
+  const uint64_t guard = 1ull << (p - 1);
   auto elem = [&](T x, bool valid) {
     if (NULLS && !valid) return;
     const uint64_t h = spark_hash<T>(x);
-    const uint32_t idx = (uint32_t)(h >> (64 - p));
-    const uint64_t w = (h << p) | (1ull << (p - 1));
+    const uint32_t idx = (uint32_t)(h >> ps);
+    const uint64_t w = (h << p) | guard;
     const uint32_t rho = (uint32_t)__clzll((long long)w) + 1u;
-    if (rho > R[idx]) atomicMax(&R[idx], rho);
+    if (SMEM) {
+      if (rho > sh[idx]) atomicMax(&sh[idx], rho);     // after warm-up almost no value raises a register
+    } else {
+      if (rho > G[idx]) atomicMax(&G[idx], rho);
+    }
   };
   const int64_t nvec = (r1 - r0) / VEC;
   const uint4* __restrict__ vdata = reinterpret_cast<const uint4*>(data + r0);
@@ -120,9 +128,8 @@ __device__ __forceinline__ void hll_tile(const HllParams& P, const anv_column_t&
       elem(data[row], valid);
     }
   }
-  if (P.use_smem) {
+  if (SMEM) {
     __syncthreads();
-    uint32_t* G = P.regs + (size_t)c * m;
     for (int i = tid; i < m; i += ANV_BLOCK) {
       const uint32_t v = sh[i];
       if (v) atomicMax(&G[i], v);
@@ -130,13 +137,14 @@ __device__ __forceinline__ void hll_tile(const HllParams& P, const anv_column_t&
   }
 }
 
+template <bool SMEM>
 __global__ void __launch_bounds__(ANV_BLOCK) hll_kernel(const HllParams P) {
   extern __shared__ __align__(16) uint32_t hll_sh[];
   const int c = blockIdx.y;
   const anv_column_t col = P.cols[c];
-#define ANV_DISPATCH(T)                                    \
-  if (col.validity) hll_tile<T, true>(P, col, c, hll_sh);  \
-  else hll_tile<T, false>(P, col, c, hll_sh);
+#define ANV_DISPATCH(T)                                          \
+  if (col.validity) hll_tile<T, true, SMEM>(P, col, c, hll_sh);  \
+  else hll_tile<T, false, SMEM>(P, col, c, hll_sh);
   switch (col.dtype) {
     case ANV_F32: ANV_DISPATCH(float) break;
     case ANV_F64: ANV_DISPATCH(double) break;
@@ -172,9 +180,10 @@ extern "C" int anv_hll_registers(const anv_column_t* cols, int n_cols, int64_t n
   P.tile_rows = (int)t;
   const size_t smem = P.use_smem ? ((size_t)4 << p) : 0;
   if (smem > 48 * 1024)
-    ANV_CUDA(cudaFuncSetAttribute(hll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ANV_CUDA(cudaFuncSetAttribute(hll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((n_rows + P.tile_rows - 1) / P.tile_rows), (unsigned)n_cols);
-  hll_kernel<<<grid, ANV_BLOCK, smem, st>>>(P);
+  if (P.use_smem) hll_kernel<true><<<grid, ANV_BLOCK, smem, st>>>(P);
+  else hll_kernel<false><<<grid, ANV_BLOCK, 0, st>>>(P);
   ANV_CUDA(cudaGetLastError());
   return ANV_OK;
 }

@@ -379,13 +379,13 @@ sort_algorithm = "lsd"            # "lsd" | "partition" (32-bit columns through 
 
 
 def _mode_distinct_batch_size(frame, n_cols, per_col_bytes):
+    """Columns per sort launch: the scratch of a batch stays under SORT_WORKSPACE_BUDGET and under 80 % of the memory that is
+    not held by live tensors (torch's allocator statistics: no driver call - cudaMemGetInfo costs ~7 ms)."""
     torch = _lib.require_cuda()
     budget = SORT_WORKSPACE_BUDGET
-    if per_col_bytes * n_cols > (4 << 30):  # cudaMemGetInfo costs ~7 ms: only ask when the scratch is large, once per frame
-        key = ("sort_budget", per_col_bytes)
-        if key not in frame._cache:
-            frame._cache[key] = min(budget, int(torch.cuda.mem_get_info()[0] * 0.8))
-        budget = frame._cache[key]
+    if per_col_bytes * n_cols > (2 << 30):
+        total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+        budget = min(budget, int((total - torch.cuda.memory_allocated()) * 0.8))
     return max(1, min(n_cols, budget // max(per_col_bytes, 1)))
 
 
@@ -454,7 +454,7 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
         for j, i in enumerate(idxs):
             if hr[j] == -3:
                 raise _lib.AnvError("anv_mode_distinct: a one-sweep look-back gave up waiting for a preceding tile (column %r); "
-                                    "set ANV_SORT_LEGACY=1 to use the three-kernel passes" % names[i])
+                                    "unset ANV_SORT_ONESWEEP to use the three-kernel passes" % names[i])
             if hr[j] == -2:               # a bucket overflowed (sampling failure): this column goes through the sort
                 redo.append(i)
                 continue

@@ -31,10 +31,12 @@ def moments(frame: ColumnFrame, names):
 
 
 def n_valid(frame: ColumnFrame, names):
-    """Non-null counts of numeric AND categorical columns (dictionary codes are I32 columns,
-    so the same fused pass counts them)."""
-    cc = frame._cache.get("codes", {})
-    have = {n: frame.n_rows - int(cc[n][0]) for n in names if n in cc and n not in frame._cache.get("moments", {})}
+    """Non-null counts.  Numeric columns: the fused moments pass.  String columns: slot 0 of their code histogram - the
+    pass that mode / distinct / HLL++ / drift need anyway, so a full stats run reads a string column once, not twice."""
+    mom_cache = frame._cache.get("moments", {})
+    cat = [n for n in names if frame.column(n).kind == "cat" and n not in mom_cache]
+    cc = code_counts(frame, cat) if cat else {}
+    have = {n: frame.n_rows - int(cc[n][0]) for n in cat}
     m = moments(frame, [n for n in names if n not in have])
     return {n: have[n] if n in have else int(m[n]["n_valid"]) for n in names}
 

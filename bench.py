@@ -48,12 +48,11 @@ WORKLOADS = {
 }
 METRIC = "rows x cols / s, full stats_generator (+ HBM GB/s of the fused scan kernel)"
 CPU_SAMPLE_ROWS = 1_000_000
-# words of HBM traffic per sorted key the sort path needs BY DESIGN: pack write 1 (the digit histograms of all
-# four passes are taken there), per one-sweep 8-bit pass {read 1 + write 1} x 4 (tile offsets by decoupled look-back: no
-# tile-histogram pass, no scan pass), run summaries read 1
-SORT_WORDS_PER_KEY = 1 + 4 * 2 + 1
-SORT_DESIGN = ("batched one-sweep 8-bit LSD radix sort + run summaries (anv_mode_distinct: pack + digit histograms, sort_bases, "
-               "4 x sort_onesweep_kernel [stable scatter with decoupled look-back], run_tile, run_merge) - exact mode / distinct / percentiles")
+# words of HBM traffic per sorted key the sort path needs BY DESIGN: pack write 1, per 8-bit pass
+# {tile histogram read 1, scatter read 1 + write 1} x 4, run summaries read 1
+SORT_WORDS_PER_KEY = 1 + 4 * 3 + 1
+SORT_DESIGN = ("batched 8-bit LSD radix sort + run summaries (anv_mode_distinct: pack, 4 x {sort_hist, sort_totals + sort_scan, "
+               "sort_scatter}, run_tile, run_merge) - exact mode / distinct / percentiles")
 # the partition + count path (anv_mode_distinct_partition, 32-bit columns): one read of the column, then every key that is not
 # a splitter value (zeros and heavy hitters are only counted) is written once to its bucket and read once by the counting CTA
 PARTITION_WORDS_PER_KEY = 2
