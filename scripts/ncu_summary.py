@@ -50,7 +50,14 @@ FRIENDLY = [
     (r"select_scan_kernel", "K4 `select_scan_kernel`"),
     (r"pack_kernel", "sort: pack keys `sort_pack_kernel`"),
     (r"sort_hist", "sort: tile digit histogram `sort_hist_kernel`"),
+    (r"sort_totals", "sort: digit totals `sort_totals_kernel`"),
     (r"sort_scan", "sort: digit/tile scan `sort_scan_kernel`"),
+    (r"sort_onesweep", "sort: one-sweep scatter `sort_onesweep_kernel` (opt-in)"),
+    (r"sort_bases", "sort: digit bases `sort_bases_kernel` (opt-in one-sweep)"),
+    (r"pc_partition", "partition path: `pc_partition_kernel` (opt-in)"),
+    (r"pc_count", "partition path: `pc_count_kernel` (opt-in)"),
+    (r"pc_", "partition path: small kernels (opt-in)"),
+    (r"spark_sample", "Spark Bernoulli sampler `spark_sample_kernel`"),
     (r"sort_scatter", "sort: stable scatter `sort_scatter_kernel`"),
     (r"run_tile", "sort: run summaries `run_tile_kernel`"),
     (r"run_merge", "sort: run merge `run_merge_kernel`"),
@@ -101,7 +108,7 @@ def full(rep, out, rows=None, cols=None):
                "lsu_pct", "xu_pct", "regs", "warps_active_pct", "warp_inst", "stall_long_scoreboard", "stall_mio_throttle",
                "stall_math_pipe"]
     with open(out + ".md", "w") as fh:
-        fh.write("# ncu --set full, round 1: per-kernel summary\n\n")
+        fh.write("# ncu --set full: per-kernel summary\n\n")
         fh.write("Source report: `%s` (`ncu --set full --clock-control none --import-source on --profile-from-start off "
                  "python scripts/prof_kernels.py`%s). Times under ncu are cold-cache and serialised; the bench numbers "
                  "come from CUDA events. DRAM bytes are `dram__bytes_read.sum` / `dram__bytes_write.sum` per launch.\n\n"
