@@ -149,6 +149,22 @@ class Column:
             dv.record_stream(consumer)
         self._dev, self._dev_valid, self._ready = dev, dv, ev
 
+    def generate_async(self, stream):
+        """Run this lazy column's generator on `stream` (a side stream) and leave an event for the consumers - the
+        counterpart of upload_async for columns that are produced on the device."""
+        torch = _lib.require_cuda()
+        if self._dev is not None or self._loader is None or stream is None:
+            return
+        consumer = torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            dev, dv = self._loader()
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        dev.record_stream(consumer)
+        if dv is not None:
+            dv.record_stream(consumer)
+        self._dev, self._dev_valid, self._ready = dev, dv, ev
+
     @property
     def has_validity(self):
         if self._loader is not None and self._dev is None:

@@ -233,10 +233,18 @@ class PartitionedFrame:
                 nxt = self._chunk_fn(i + 1)
                 for n in (names or nxt.columns):
                     c = nxt.column(n)
-                    if c.kind != "other" and c._dev is None and c._host is not None:
+                    if c.kind == "other" or c._dev is not None:
+                        continue
+                    if c._host is not None:
                         if copy is None:
                             copy = torch.cuda.Stream()
                         c.upload_async(copy)
+                    elif c._loader is not None:
+                        # generated chunks (synthetic frames): run the generator of chunk i+1 on the side stream while the
+                        # scan kernels of chunk i run - the generator is ALU-bound, the scans HBM-bound
+                        if copy is None:
+                            copy = torch.cuda.Stream()
+                        c.generate_async(copy)
             yield cur
             if self._release:
                 for n in cur.columns:
