@@ -64,6 +64,7 @@ _SIGNATURES = {
     "anv_xxh64_utf8": (C.c_int, [_P, _P, _L, _P]),
     "anv_mode_distinct_workspace_bytes": (_SZ, [_I, _L, _I]),
     "anv_mode_distinct": (C.c_int, [_P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _SZ, _P]),
+    "anv_mode_distinct_hll": (C.c_int, [_P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _SZ, _P]),
     "anv_mode_distinct_partition_workspace_bytes": (_SZ, [_I, _L]),
     "anv_mode_distinct_partition": (C.c_int, [_P, _I, _L, _P, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "anv_spark_hash_seed": (C.c_uint64, [_L]),

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "hll_hash.cuh"
 
 namespace anv {
 
@@ -62,6 +63,26 @@ __device__ __forceinline__ double sorted_key_to_double(uint64_t k, int dtype) {
   }
 }
 
+// Spark's hash of the VALUE a sorted key stands for (the HLL++ by-product of the run summaries): undo the order-preserving
+// transform; every NaN has the key ~0 and hashes as the canonical NaN, like Spark's floatToIntBits / doubleToLongBits.
+template <typename K> __device__ __forceinline__ uint64_t spark_hash_of_key(K k, int dtype);
+template <> __device__ __forceinline__ uint64_t spark_hash_of_key<uint32_t>(uint32_t k, int dtype) {
+  if (dtype == ANV_I32) return xxh64_int(k ^ 0x80000000u);
+  const uint32_t u = (k == 0xFFFFFFFFu) ? 0x7fc00000u : ((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+  return xxh64_int(u);
+}
+template <> __device__ __forceinline__ uint64_t spark_hash_of_key<uint64_t>(uint64_t k, int dtype) {
+  switch (dtype) {
+    case ANV_F32: return spark_hash_of_key<uint32_t>((uint32_t)(k >> 32), ANV_F32);
+    case ANV_I32: return spark_hash_of_key<uint32_t>((uint32_t)(k >> 32), ANV_I32);
+    case ANV_I64: return xxh64_long(k ^ (1ull << 63));
+    default: {
+      const uint64_t u = (k == ~0ull) ? 0x7ff8000000000000ull : ((k >> 63) ? (k & ~(1ull << 63)) : ~k);
+      return xxh64_long(u);
+    }
+  }
+}
+
 struct ColState {               // one per column, in the workspace
   unsigned long long n_valid;   // filled by pack_kernel: non-null, NONZERO values = keys that are sorted
   unsigned long long n_zero;    // filled by pack_kernel: non-null values equal to 0 (kept out of the sort, see pack)
@@ -92,6 +113,9 @@ template <typename K> struct SortParams {
   uint32_t* gbase;              // [n_cols][sizeof(K)][256]  their exclusive scans
   unsigned long long* status;   // [n_cols][n_tiles][256]   (epoch << 56 | kind << 54 | count): tile aggregates / inclusive prefixes
   uint32_t* ticket;             // [n_cols][sizeof(K)]       tile ids are handed out in arrival order
+  // optional by-product: HyperLogLog++ registers (Spark's approx_count_distinct) from the DISTINCT sorted keys
+  int hll_p;                    // 0 = off; 4..12
+  uint32_t* hll_regs;           // [n_cols][1 << hll_p], zeroed by the host wrapper
 };
 constexpr int PACK_TPC = 8;     // tiles per pack CTA (amortises the flush of the digit histograms)
 
@@ -671,6 +695,30 @@ __global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K>
   s.last_key = last;
   s.suffix_len = m ? run : 0;
   if (s.heads_inside == 0) s.prefix_len = m;
+  // HLL++ by-product: the registers are a max over the SET of values, so hashing one key per run (plus this thread's first
+  // key, whose run may have started in the previous thread - a harmless repeat) replaces the pass over all values
+  extern __shared__ __align__(16) uint32_t hll_sh[];
+  const int hp = P.hll_p;
+  if (hp) {
+    const int hm = 1 << hp;
+    for (int i = tid; i < hm; i += ANV_BLOCK) hll_sh[i] = 0;
+    __syncthreads();
+    const int dt = P.cols[c].dtype;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (j < m && (j == 0 || k[j] != k[j - 1])) {
+        uint32_t idx, rho;
+        hll_slot(spark_hash_of_key<K>(k[j], dt), hp, idx, rho);
+        if (rho > hll_sh[idx]) atomicMax(&hll_sh[idx], rho);
+      }
+    }
+    __syncthreads();
+    uint32_t* G = P.hll_regs + ((size_t)c << hp);
+    for (int i = tid; i < hm; i += ANV_BLOCK) {
+      const uint32_t v = hll_sh[i];
+      if (v && v > G[i]) atomicMax(&G[i], v);       // the registers saturate after a few tiles: almost no atomics later
+    }
+  }
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const TileSummary<K> right = shfl_down_summary(s, o);
@@ -721,6 +769,11 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
       v = sorted_key_to_double(sizeof(K) == 8 ? (uint64_t)k : ((uint64_t)k << 32), dt);
     }
     rank_values[(size_t)c * n_ranks + r] = v;
+  }
+  if (P.hll_p && nz > 0 && lane == 0) {   // the zero run never reached the sort: its value hashes here
+    uint32_t idx, rho;
+    hll_slot(spark_hash_of_key<K>(ZERO_KEY, dt), P.hll_p, idx, rho);
+    atomicMax(&P.hll_regs[((size_t)c << P.hll_p) + idx], rho);
   }
   if (S.error) {                      // a look-back gave up: make the host raise (results would be garbage)
     if (lane == 0) { mode_value[c] = nan(""); mode_rows[c] = -3; n_distinct[c] = -3; }
@@ -785,8 +838,8 @@ template <typename K> struct Layout {
 
 template <typename K>
 static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, double* mode_value, int64_t* mode_rows,
-                             int64_t* n_distinct, const int64_t* ranks, int n_ranks, double* rank_values, void* workspace,
-                             size_t workspace_bytes, cudaStream_t st) {
+                             int64_t* n_distinct, const int64_t* ranks, int n_ranks, double* rank_values, int hll_p,
+                             uint32_t* hll_regs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   Layout<K> L(n_cols, n_rows);
   if (workspace_bytes < L.total) { set_error("anv_mode_distinct: workspace too small (%zu < %zu)", workspace_bytes, L.total); return ANV_ERR_WORKSPACE; }
   char* w = reinterpret_cast<char*>(workspace);
@@ -805,6 +858,9 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   P.gbase = reinterpret_cast<uint32_t*>(w + L.gbase);
   P.ticket = reinterpret_cast<uint32_t*>(w + L.ticket);
   P.status = reinterpret_cast<unsigned long long*>(w + L.status);
+  P.hll_p = hll_regs ? hll_p : 0;
+  P.hll_regs = hll_regs;
+  if (hll_regs) ANV_CUDA(cudaMemsetAsync(hll_regs, 0, ((size_t)n_cols << hll_p) * sizeof(uint32_t), st));
   // Default: three kernels per pass (tile histogram, (digit, column)-parallel scan, stable scatter).  ANV_SORT_ONESWEEP=1 selects the
   // one-sweep passes for 32-bit keys (digit histograms in pack + decoupled look-back in the scatter: 10 instead of 14 words of
   // traffic per key).  Measured on B200 (c2, 4e8 keys): 3.06 ms per one-sweep pass against 2.19 ms for the three kernels - the
@@ -839,7 +895,7 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
         ANV_CUDA(cudaGetLastError());
       }
     }
-    run_tile_kernel<K><<<grid, ANV_BLOCK, 0, st>>>(P);
+    run_tile_kernel<K><<<grid, ANV_BLOCK, P.hll_p ? ((size_t)4 << P.hll_p) : 0, st>>>(P);
     ANV_CUDA(cudaGetLastError());
   }
   run_merge_kernel<K><<<n_cols, 32, 0, st>>>(P, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values);
@@ -1344,18 +1400,27 @@ extern "C" size_t anv_mode_distinct_workspace_bytes(int n_cols, int64_t n_rows, 
   return key_bits == 32 ? Layout<uint32_t>(n_cols, n_rows).total : Layout<uint64_t>(n_cols, n_rows).total;
 }
 
-extern "C" int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, int key_bits, double* mode_value,
-                                 int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks, int n_ranks,
-                                 double* rank_values, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int anv_mode_distinct_hll(const anv_column_t* cols, int n_cols, int64_t n_rows, int key_bits, double* mode_value,
+                                     int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks, int n_ranks,
+                                     double* rank_values, int hll_p, uint32_t* hll_regs, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
   if (n_ranks < 0 || (n_ranks > 0 && (!ranks || !rank_values))) { set_error("anv_mode_distinct: bad ranks arguments"); return ANV_ERR_INVALID; }
   if (n_cols < 0 || n_rows < 0 || (key_bits != 32 && key_bits != 64)) { set_error("anv_mode_distinct: bad arguments"); return ANV_ERR_INVALID; }
+  if (hll_regs && (hll_p < 4 || hll_p > 12)) { set_error("anv_mode_distinct_hll: 4 <= hll_p <= 12"); return ANV_ERR_INVALID; }
   if (n_cols == 0) return ANV_OK;
   if (n_cols > 65535) { set_error("n_cols > 65535"); return ANV_ERR_UNSUPPORTED; }
   if (n_rows >= ((int64_t)1 << 32)) { set_error("anv_mode_distinct: n_rows >= 2^32 per call is not supported"); return ANV_ERR_UNSUPPORTED; }
   if (!cols || !mode_value || !mode_rows || !n_distinct || !workspace) { set_error("anv_mode_distinct: NULL argument"); return ANV_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (key_bits == 32) return run_mode_distinct<uint32_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, workspace, workspace_bytes, st);
-  return run_mode_distinct<uint64_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, workspace, workspace_bytes, st);
+  if (key_bits == 32) return run_mode_distinct<uint32_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, hll_p, hll_regs, workspace, workspace_bytes, st);
+  return run_mode_distinct<uint64_t>(cols, n_cols, n_rows, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, hll_p, hll_regs, workspace, workspace_bytes, st);
+}
+
+extern "C" int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, int key_bits, double* mode_value,
+                                 int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks, int n_ranks,
+                                 double* rank_values, void* workspace, size_t workspace_bytes, void* stream) {
+  return anv_mode_distinct_hll(cols, n_cols, n_rows, key_bits, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values, 0,
+                               nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t anv_mode_distinct_partition_workspace_bytes(int n_cols, int64_t n_rows) {

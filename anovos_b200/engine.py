@@ -376,6 +376,7 @@ def select_ranks(frame: ColumnFrame, names, ranks):
 
 SORT_WORKSPACE_BUDGET = 24 << 30  # bytes of scratch one sort batch may use
 sort_algorithm = "lsd"            # "lsd" | "partition" (32-bit columns through anv_mode_distinct_partition; tests run both)
+FUSED_HLL = True                  # sort_mode_distinct(..., hll_p=p) also returns the HLL++ registers (hashed from the sorted runs)
 
 
 def _mode_distinct_batch_size(frame, n_cols, per_col_bytes):
@@ -389,8 +390,11 @@ def _mode_distinct_batch_size(frame, n_cols, per_col_bytes):
     return max(1, min(n_cols, budget // max(per_col_bytes, 1)))
 
 
-def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
+def sort_mode_distinct(frame: ColumnFrame, names, ranks=None, hll_p=None):
     """-> list of (mode value | None, mode_rows | None, n_distinct) for NUMERIC columns.
+    hll_p (4..12, LSD path only): additionally returns the HyperLogLog++ registers uint32 [n_cols, 2**hll_p] as a by-product
+    of the run summaries (one hash per DISTINCT value instead of a separate pass over every value) - the result then is
+    (list, rank values | None, registers).
     ranks: optional int64 [n_cols, n_ranks] of 1-based ranks among the non-null values (0 = skip);
     then returns (list, float64 [n_cols, n_ranks]) with the exact order statistics.
     Default: the batched LSD radix sort (anv_mode_distinct).  sort_algorithm = "partition" sends 32-bit columns through
@@ -409,6 +413,9 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
         ranks = np.ascontiguousarray(ranks, dtype=np.int64).reshape(len(names), -1)
         n_ranks = ranks.shape[1]
     rvals = np.full((len(names), n_ranks), np.nan, np.float64)
+    want_hll = hll_p is not None and 4 <= hll_p <= 12 and sort_algorithm == "lsd"
+    hll_m = (1 << hll_p) if want_hll else 0
+    hregs = np.zeros((len(names), hll_m), np.uint32) if want_hll else None
     res = {}
     groups = {}
     for i, nme in enumerate(names):
@@ -428,6 +435,7 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
         # one result block for the whole call: [mode_value | mode_rows | n_distinct | rank_values], 8 bytes per cell
         out = torch.empty((3 + n_ranks) * n_all, dtype=torch.int64, device="cuda")
         base = out.data_ptr()
+        dregs = torch.empty(max(n_all * hll_m, 1), dtype=torch.int32, device="cuda") if (want_hll and not partition) else None
         drk = _to_dev(ranks[idxs]) if n_ranks else None
         for b0 in range(0, n_all, batch):
             sub = [names[i] for i in idxs[b0:b0 + batch]]
@@ -441,14 +449,17 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
                       *common, nbytes=input_bytes(frame, sub))
                 launch_count += 6 + 16
             else:
-                _call(L.anv_mode_distinct, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv, mr, nd,
-                      *common, nbytes=input_bytes(frame, sub))
+                _call(L.anv_mode_distinct_hll, "anv_mode_distinct", desc.data_ptr(), n, frame.n_rows, kb, mv, mr, nd,
+                      *common[:3], hll_p if dregs is not None else 0,
+                      dregs.data_ptr() + b0 * hll_m * 4 if dregs is not None else None, *common[3:], nbytes=input_bytes(frame, sub))
                 launch_count += 3 + 4 * (kb // 8)
         host = _host(out.view(torch.uint8))
         hv = host[:n_all * 8].view(np.float64)
         hr = host[n_all * 8:2 * n_all * 8].view(np.int64)
         hd = host[2 * n_all * 8:3 * n_all * 8].view(np.int64)
         hrv = host[3 * n_all * 8:].view(np.float64).reshape(n_all, n_ranks) if n_ranks else None
+        if dregs is not None:
+            hregs[np.asarray(idxs)] = _host(dregs.view(torch.uint8)).view(np.uint32)[:n_all * hll_m].reshape(n_all, hll_m)
         del ws
         redo = []
         for j, i in enumerate(idxs):
@@ -469,6 +480,8 @@ def sort_mode_distinct(frame: ColumnFrame, names, ranks=None):
         if idxs:
             run(kb, idxs, False)
     out = [res[n] for n in names]
+    if hll_p is not None:
+        return out, (rvals if ranks is not None else None), hregs
     return (out, rvals) if ranks is not None else out
 
 

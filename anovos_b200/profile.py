@@ -13,6 +13,7 @@ from .shared.gk import APPROX_QUANTILE_EPS, SUMMARY_EPS
 
 
 SUMMARY_PROBS = [0.01, 0.05, 0.1, 0.25, 0.5, 0.75, 0.9, 0.95, 0.99]
+DEFAULT_HLL_P = 9     # approx_count_distinct's default rsd = 0.05 -> p = ceil(2 log2(1.106 / 0.05)) = 9
 
 
 def _cache(frame: ColumnFrame, key):
@@ -123,7 +124,17 @@ def mode_distinct(frame: ColumnFrame, names):
         mom = moments(frame, num)
         qc = _cache(frame, "quantiles")
         rk = np.array([engine.quantile_ranks(int(mom[n]["n_valid"]), SUMMARY_PROBS, SUMMARY_EPS) for n in num], dtype=np.int64)
-        res, vals = engine.sort_mode_distinct(frame, num, rk)
+        # ... and the HyperLogLog++ registers of the default rsd (p = 9) come out of the same pass: the run summaries hash one
+        # key per distinct value, so a following measures_of_cardinality() needs no pass of its own
+        fused_p = DEFAULT_HLL_P if (getattr(engine, "FUSED_HLL", False) and not getattr(frame, "is_partitioned", False)) else None
+        if fused_p is not None:
+            res, vals, regs = engine.sort_mode_distinct(frame, num, rk, hll_p=fused_p)
+            if regs is not None:
+                hc = _cache(frame, ("hll", fused_p))
+                for n, r in zip(num, engine.hll_estimates_from_register_rows(regs, fused_p)):
+                    hc.setdefault(n, r)
+        else:
+            res, vals = engine.sort_mode_distinct(frame, num, rk)
         for i, n in enumerate(num):
             c[n] = res[i]
             for r, v in zip(rk[i], vals[i]):

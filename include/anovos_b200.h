@@ -189,6 +189,14 @@ int anv_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_rows, int 
                       double* mode_value, int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks,
                       int n_ranks, double* rank_values, void* workspace, size_t workspace_bytes, void* stream);
 
+/* anv_mode_distinct + the HyperLogLog++ registers of the same columns as a by-product (hll_regs [dev] (n_cols << hll_p)
+ * uint32, 4 <= hll_p <= 12; NULL = off): the registers are a max over the SET of values, so the run-summary kernel hashes ONE
+ * key per run of the sorted keys instead of a separate pass hashing every value (anv_hll_registers; stats_generator.py:
+ * 605-608 next to :386-401).  Registers are identical to anv_hll_registers'. */
+int anv_mode_distinct_hll(const anv_column_t* cols, int n_cols, int64_t n_rows, int key_bits, double* mode_value,
+                          int64_t* mode_rows, int64_t* n_distinct, const int64_t* ranks, int n_ranks, double* rank_values,
+                          int hll_p, uint32_t* hll_regs, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The same results for F32 / I32 columns WITHOUT sorting them (sort.cu, "partition + count"): sample -> splitters ->
  * one partition pass over the raw column (keys equal to a splitter - zeros, heavy hitters, discrete values - are only
  * counted) -> per-bucket shared-memory hash tables (multiplicities) and in-bucket radix select for the requested ranks.

@@ -229,6 +229,7 @@ def installed():
              "hll_registers", "bin_assign"]
     saved = {n: getattr(engine, n) for n in names}
     saved_req, saved_up, saved_dev = _lib.require_cuda, framemod.Column.upload_async, framemod.Column.device
+    saved_fused, engine.FUSED_HLL = engine.FUSED_HLL, False
     from anovos_b200.data_ingest import data_sampling
     saved_mask = data_sampling.sample_mask
     try:
@@ -245,3 +246,4 @@ def installed():
             setattr(engine, n, f)
         _lib.require_cuda, framemod.Column.upload_async, framemod.Column.device = saved_req, saved_up, saved_dev
         data_sampling.sample_mask = saved_mask
+        engine.FUSED_HLL = saved_fused

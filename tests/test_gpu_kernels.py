@@ -385,3 +385,28 @@ def test_partition_count_adversarial_columns(n, monkeypatch):
         assert got[i][2] == u.size and got[i][1] == int(k.max()), c
         best = u[k == k.max()]
         assert got[i][0] == float(np.nanmin(best)) or (np.isnan(got[i][0]) and np.isnan(best).all()), c
+
+
+@pytest.mark.parametrize("n", [1, 777, 250_003])
+def test_hll_registers_from_the_sorted_runs_equal_the_hll_kernel(n):
+    """anv_mode_distinct_hll: the registers hashed from one key per run of the sorted keys (+ the zero run) are the
+    registers anv_hll_registers computes from every value - all dtypes, nulls, zeros, -0.0, NaN, 32- and 64-bit key groups."""
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    rng = np.random.default_rng(n)
+    f = rng.normal(0, 3, n).astype(np.float32)
+    f[rng.random(n) < 0.2] = 0.0
+    f[rng.random(n) < 0.05] = -0.0
+    f[rng.random(n) < 0.03] = np.nan
+    d = np.round(rng.normal(-1e6, 250, n), 1)
+    d[rng.random(n) < 0.02] = np.nan
+    t = pa.table({"f32": pa.array(f, mask=rng.random(n) < 0.1), "i32": pa.array(rng.integers(-5, 6, n).astype(np.int32)),
+                  "f64": pa.array(d, mask=rng.random(n) < 0.3), "i64": pa.array(rng.integers(-2 ** 40, 2 ** 40, n)),
+                  "all_null": pa.array(np.zeros(n, np.float32), mask=np.ones(n, bool)),
+                  "wide": pa.array(rng.normal(0, 1e3, n).astype(np.float32))})
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    for p in (9, 12):
+        res, _, regs = engine.sort_mode_distinct(fr, names, None, hll_p=p)
+        assert res == engine.sort_mode_distinct(fr, names) or all(a[1:] == b[1:] for a, b in zip(res, engine.sort_mode_distinct(fr, names)))
+        assert np.array_equal(regs, engine.hll_registers(fr, names, p)), p
