@@ -209,11 +209,15 @@ __device__ __forceinline__ void pack_tile(const SortParams<K>& P, const anv_colu
   const uint32_t total = s_total;
   // copy-out + the digit histograms of EVERY pass from the staged keys (the one-sweep passes need the column-wide digit counts
   // before the first scatter; taking them here replaces one full read of the keys per pass)
-  for (uint32_t i = tid; i < total; i += ANV_BLOCK) {
-    const K k = sk[i];
-    out[i] = k;
+  if (P.ghist) {
+    for (uint32_t i = tid; i < total; i += ANV_BLOCK) {
+      const K k = sk[i];
+      out[i] = k;
 #pragma unroll
-    for (int ps = 0; ps < (int)sizeof(K); ++ps) atomicAdd(&s_dh[ps][digit_of(k, ps)], 1u);
+      for (int ps = 0; ps < (int)sizeof(K); ++ps) atomicAdd(&s_dh[ps][digit_of(k, ps)], 1u);
+    }
+  } else {
+    for (uint32_t i = tid; i < total; i += ANV_BLOCK) out[i] = sk[i];
   }
   __syncthreads();   // sk / s_warp are reused by the CTA's next tile
 }
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(ANV_BLOCK) pack_kernel(const SortParams<K> P) 
       default: break;
     }
   }
+  if (!P.ghist) return;
   __syncthreads();
   uint32_t* g = P.ghist + (size_t)c * sizeof(K) * 256;
 #pragma unroll
@@ -700,17 +705,37 @@ __global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K>
   extern __shared__ __align__(16) uint32_t hll_sh[];
   const int hp = P.hll_p;
   if (hp) {
+    // The run heads are first COMPACTED into shared memory (a thread holds between 1 and 16 of them: hashing in place would
+    // keep every warp busy for the maximum over its lanes), then hashed by full warps.
     const int hm = 1 << hp;
+    K* hk = reinterpret_cast<K*>(hll_sh + hm);                 // [SORT_TILE] head keys
+    __shared__ uint32_t s_hw[ANV_WARPS + 1];
     for (int i = tid; i < hm; i += ANV_BLOCK) hll_sh[i] = 0;
-    __syncthreads();
-    const int dt = P.cols[c].dtype;
+    uint32_t hcnt = 0;
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      if (j < m && (j == 0 || k[j] != k[j - 1])) {
-        uint32_t idx, rho;
-        hll_slot(spark_hash_of_key<K>(k[j], dt), hp, idx, rho);
-        if (rho > hll_sh[idx]) atomicMax(&hll_sh[idx], rho);
-      }
+    for (int j = 0; j < PER; ++j) hcnt += (j < m && (j == 0 || k[j] != k[j - 1])) ? 1u : 0u;
+    uint32_t inc = hcnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(ANV_FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_hw[warp] = inc;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t acc = 0;
+      for (int w2 = 0; w2 < ANV_WARPS; ++w2) { const uint32_t t = s_hw[w2]; s_hw[w2] = acc; acc += t; }
+      s_hw[ANV_WARPS] = acc;
+    }
+    __syncthreads();
+    uint32_t at = s_hw[warp] + inc - hcnt;
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+      if (j < m && (j == 0 || k[j] != k[j - 1])) hk[at++] = k[j];
+    __syncthreads();
+    const uint32_t n_heads = s_hw[ANV_WARPS];
+    const int dt = P.cols[c].dtype;
+    for (uint32_t i = tid; i < n_heads; i += ANV_BLOCK) {
+      uint32_t idx, rho;
+      hll_slot(spark_hash_of_key<K>(hk[i], dt), hp, idx, rho);
+      if (rho > hll_sh[idx]) atomicMax(&hll_sh[idx], rho);
     }
     __syncthreads();
     uint32_t* G = P.hll_regs + ((size_t)c << hp);
@@ -854,7 +879,7 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   P.tile_hist = reinterpret_cast<uint32_t*>(w + L.tile_hist);
   P.summ = reinterpret_cast<TileSummary<K>*>(w + L.summ);
   uint32_t* totals = reinterpret_cast<uint32_t*>(w + L.totals);
-  P.ghist = reinterpret_cast<uint32_t*>(w + L.ghist);
+  P.ghist = nullptr;                                   // set below when the one-sweep passes are selected
   P.gbase = reinterpret_cast<uint32_t*>(w + L.gbase);
   P.ticket = reinterpret_cast<uint32_t*>(w + L.ticket);
   P.status = reinterpret_cast<unsigned long long*>(w + L.status);
@@ -869,7 +894,10 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
   const char* os_env = getenv("ANV_SORT_ONESWEEP");
   const bool legacy = !(os_env && os_env[0] == '1') || sizeof(K) != 4;
   ANV_CUDA(cudaMemsetAsync(P.state, 0, (size_t)n_cols * sizeof(ColState), st));
-  ANV_CUDA(cudaMemsetAsync(w + L.ghist, 0, legacy ? L.status - L.ghist : L.total - 256 - L.ghist, st));
+  if (!legacy) {
+    P.ghist = reinterpret_cast<uint32_t*>(w + L.ghist);
+    ANV_CUDA(cudaMemsetAsync(w + L.ghist, 0, L.total - 256 - L.ghist, st));   // digit counts, bases, tickets, look-back status
+  }
   if (n_rows > 0) {
     dim3 grid(P.n_tiles, n_cols);
     pack_kernel<K><<<dim3((P.n_tiles + PACK_TPC - 1) / PACK_TPC, n_cols), ANV_BLOCK, 0, st>>>(P);
@@ -895,7 +923,9 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
         ANV_CUDA(cudaGetLastError());
       }
     }
-    run_tile_kernel<K><<<grid, ANV_BLOCK, P.hll_p ? ((size_t)4 << P.hll_p) : 0, st>>>(P);
+    const size_t run_smem = P.hll_p ? ((size_t)4 << P.hll_p) + (size_t)SORT_TILE * sizeof(K) : 0;   // registers + head keys
+    if (run_smem > 48 * 1024) ANV_CUDA(cudaFuncSetAttribute(run_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run_smem));
+    run_tile_kernel<K><<<grid, ANV_BLOCK, run_smem, st>>>(P);
     ANV_CUDA(cudaGetLastError());
   }
   run_merge_kernel<K><<<n_cols, 32, 0, st>>>(P, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values);

@@ -81,7 +81,10 @@ def to_float(cell):
 
 
 def full(rep, out, rows=None, cols=None):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):     # `ncu -i <rep> --page raw --csv` already run on the GPU box (a full report can exceed the 64 MiB pull limit)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows_csv = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows_csv[0], rows_csv[1]
     idx = {m: hdr.index(m) for _, m in METRICS if m in hdr}
