@@ -763,11 +763,12 @@ __global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K>
 // One warp per column: 32 tile summaries per step are combined with an order-preserving
 // shuffle tree, the chunk results sequentially by lane 0.  Also reads the requested order
 // statistics straight out of the sorted keys.
+constexpr int MERGE_WARPS = 8;
 template <typename K>
-__global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, double* mode_value, int64_t* mode_rows,
+__global__ void __launch_bounds__(32 * MERGE_WARPS) run_merge_kernel(const SortParams<K> P, double* mode_value, int64_t* mode_rows,
                                                        int64_t* n_distinct, const int64_t* ranks, int n_ranks,
                                                        double* rank_values) {
-  const int c = blockIdx.x, lane = threadIdx.x;
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const ColState& S = P.state[c];
   const int64_t n = (int64_t)S.n_valid;      // sorted (nonzero) keys
   const int64_t nz = (int64_t)S.n_zero;      // the zero run that pack_kernel kept out of the sort
@@ -783,7 +784,7 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
     }
     below = lo;
   }
-  for (int r = lane; r < n_ranks; r += 32) {
+  for (int r = tid; r < n_ranks; r += 32 * MERGE_WARPS) {
     const int64_t rk = ranks[(size_t)c * n_ranks + r];
     double v = nan("");
     if (rk > 0 && rk <= n + nz) {
@@ -795,17 +796,17 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
     }
     rank_values[(size_t)c * n_ranks + r] = v;
   }
-  if (P.hll_p && nz > 0 && lane == 0) {   // the zero run never reached the sort: its value hashes here
+  if (P.hll_p && nz > 0 && tid == 0) {   // the zero run never reached the sort: its value hashes here
     uint32_t idx, rho;
     hll_slot(spark_hash_of_key<K>(ZERO_KEY, dt), P.hll_p, idx, rho);
     atomicMax(&P.hll_regs[((size_t)c << P.hll_p) + idx], rho);
   }
   if (S.error) {                      // a look-back gave up: make the host raise (results would be garbage)
-    if (lane == 0) { mode_value[c] = nan(""); mode_rows[c] = -3; n_distinct[c] = -3; }
+    if (tid == 0) { mode_value[c] = nan(""); mode_rows[c] = -3; n_distinct[c] = -3; }
     return;
   }
   if (n == 0) {
-    if (lane == 0) {
+    if (tid == 0) {
       mode_value[c] = nz ? sorted_key_to_double(sizeof(K) == 8 ? (uint64_t)ZERO_KEY : ((uint64_t)ZERO_KEY << 32), dt) : nan("");
       mode_rows[c] = nz;
       n_distinct[c] = nz ? 1 : 0;
@@ -814,12 +815,17 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
   }
   const TileSummary<K>* T = P.summ + (size_t)c * P.n_tiles;
   const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
+  // every warp folds a contiguous range of tile summaries (order-preserving shuffle tree over 32 at a time), warp 0 then
+  // folds the warp results in order: 8 warps instead of one walk the 24 K summaries of a 100 M-row column
+  const int wid = tid >> 5;
+  const int per_warp = (tiles + MERGE_WARPS - 1) / MERGE_WARPS;
+  const int w_lo = wid * per_warp, w_hi = min(tiles, w_lo + per_warp);
   TileSummary<K> acc;
   acc.n = 0;
-  for (int t0 = 0; t0 < tiles; t0 += 32) {
+  for (int t0 = w_lo; t0 < w_hi; t0 += 32) {
     TileSummary<K> mine;
     mine.n = 0;
-    if (t0 + lane < tiles) mine = T[t0 + lane];
+    if (t0 + lane < w_hi) mine = T[t0 + lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const TileSummary<K> right = shfl_down_summary(mine, o);
@@ -827,6 +833,12 @@ __global__ void __launch_bounds__(32) run_merge_kernel(const SortParams<K> P, do
     }
     if (lane == 0) acc = combine(acc, mine);
   }
+  __shared__ TileSummary<K> s_acc[MERGE_WARPS];
+  if (lane == 0) s_acc[wid] = acc;
+  __syncthreads();
+  if (tid != 0) return;
+  acc = s_acc[0];
+  for (int w2 = 1; w2 < MERGE_WARPS; ++w2) acc = combine(acc, s_acc[w2]);
   if (lane == 0) {
     K bk = 0; uint32_t bl = 0;
     best_of(bk, bl, acc.first_key, acc.prefix_len);
@@ -928,7 +940,7 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
     run_tile_kernel<K><<<grid, ANV_BLOCK, run_smem, st>>>(P);
     ANV_CUDA(cudaGetLastError());
   }
-  run_merge_kernel<K><<<n_cols, 32, 0, st>>>(P, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values);
+  run_merge_kernel<K><<<n_cols, 32 * MERGE_WARPS, 0, st>>>(P, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values);
   ANV_CUDA(cudaGetLastError());
   return ANV_OK;
 }
