@@ -25,6 +25,9 @@
 
 namespace anv {
 
+#ifndef ANV_SCAT_MINB
+#define ANV_SCAT_MINB 2          // resident scatter CTAs per SM the register budget is tuned for
+#endif
 constexpr int SORT_TILE = 4096;  // keys per CTA
 constexpr int SCAT_THREADS = 512;  // the scatter kernel runs 16 warps x 8 rounds of 32 keys
 constexpr int SCAT_WARPS = SCAT_THREADS / 32;
@@ -573,7 +576,7 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
 }
 
 template <typename K>
-__global__ void __launch_bounds__(SCAT_THREADS, 2) sort_scatter_kernel(const SortParams<K> P) {
+__global__ void __launch_bounds__(SCAT_THREADS, ANV_SCAT_MINB) sort_scatter_kernel(const SortParams<K> P) {
   const int c = blockIdx.y, tile = blockIdx.x;
   const ColState& S = P.state[c];
   if (S.skip[P.pass]) return;
@@ -936,7 +939,8 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
       }
     }
     const size_t run_smem = P.hll_p ? ((size_t)4 << P.hll_p) + (size_t)SORT_TILE * sizeof(K) : 0;   // registers + head keys
-    if (run_smem > 48 * 1024) ANV_CUDA(cudaFuncSetAttribute(run_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run_smem));
+    if (run_smem > 40 * 1024)    // dynamic + the kernel's static shared memory must stay under the default 48 KB otherwise
+      ANV_CUDA(cudaFuncSetAttribute(run_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run_smem));
     run_tile_kernel<K><<<grid, ANV_BLOCK, run_smem, st>>>(P);
     ANV_CUDA(cudaGetLastError());
   }
