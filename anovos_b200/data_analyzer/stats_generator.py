@@ -234,13 +234,14 @@ def measures_of_centralTendency(spark, idf, list_of_cols="all", drop_cols=[], pr
     fr = as_frame(idf)
     cols = _discrete_cols(fr, list_of_cols, drop_cols)
     num = [c for c in cols if fr.column(c).kind == "num"]
-    m = profile.moments(fr, cols)
+    m = profile.moments(fr, num)
+    nvd = profile.n_valid(fr, cols)             # string columns: from their code histogram (no second pass over them)
     md = profile.mode_distinct(fr, cols)       # the sort also yields the exact percentiles (cached)
     med = profile.quantiles(fr, num, [0.5])
     rows = []
     for c in cols:
         col = fr.column(c)
-        nv = int(m[c]["n_valid"])
+        nv = nvd[c]
         mean = median = None
         if col.kind == "num" and nv:
             mean = _R(float(m[c]["mean"]))
