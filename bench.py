@@ -265,7 +265,7 @@ def _run_ours(args, out):
         try:  # dram__bytes_read+write per call from a committed ncu capture of the SAME workload
             tj = json.load(open(os.path.join(ROOT, "profiles", cand)))
             if tj.get("rows") == rows and tj.get("cols") == cols and tj.get("cat_every", 0) == cat_every:
-                traffic_tbl, traffic_src = tj["dram_bytes_per_step"], "profiles/" + cand
+                traffic_tbl, traffic_src = tj["dram_bytes_per_launch"], "profiles/" + cand
                 break
         except Exception:
             pass
@@ -285,7 +285,7 @@ def _run_ours(args, out):
                 "call": call,
                 "bound": BOUND.get(call, "hbm"), "achieved": ach, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak if ach else None,
-                "traffic": traffic / per_step if traffic else None, "traffic_source": traffic_src if traffic else None,
+                "traffic": traffic if traffic else None, "traffic_source": traffic_src if traffic else None,
                 "algorithmic_bytes_per_launch": alg / per_step if alg else None,
                 "ms_per_launch": ms_step / per_step, "launches_per_step": per_step,
                 "share_of_step": v["ms"] / ms if ms > 0 else None}

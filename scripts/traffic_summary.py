@@ -24,6 +24,12 @@ CALL_OF = [  # first match wins
 ]
 
 
+# one launch of these kernels = one C call (to turn the capture into bytes per CALL, whatever the number of calls per step)
+CALL_MARK = {"anv_moments": r"finalize_moments", "anv_mode_distinct": r"run_merge", "anv_mode_distinct_partition": r"pc_final",
+             "anv_hll_registers": r"hll_kernel", "anv_hist_codes": r"scan_kernel<\(bool\)0|scan_kernel<0", "anv_moments_hist": r"finalize_moments",
+             "anv_select_ranks": None, "anv_drift_reduce": r"drift_reduce"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("csv")
@@ -59,7 +65,13 @@ def main():
         calls[call]["bytes"] += tr
         calls[call]["ms"] += v["ms"]
         rows.append((k, call, launches[k], v["ms"], tr))
+    n_calls = {}
+    for call, pat in CALL_MARK.items():
+        if pat and call in calls:
+            n_calls[call] = sum(n for k, n in launches.items() if re.search(pat, k)) or None
     out = {"workload_rows": a.rows, "rows": a.rows, "cols": a.cols, "cat_every": a.cat_every, "steps_captured": a.steps,
+           "calls_captured": n_calls,
+           "dram_bytes_per_launch": {c: calls[c]["bytes"] / n for c, n in n_calls.items() if n},
            "source": a.csv + " (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none; "
                      + (a.command or "bench.py --no-extras") + "); bytes of every kernel a C call launches, per step; times are ncu's "
                      "serialised cold-cache times: compare shares, not absolutes",
