@@ -41,6 +41,18 @@ def _empty(cols):
     return ResultFrame(pd.DataFrame({c: pd.Series([], dtype=object) for c in cols}))
 
 
+def _opt(a):
+    """float64 array with NaN = null -> column for a result frame: stays float64 when nothing is null, else object with None
+    (what the row-wise construction produced: the reference frames hold nulls, not NaNs)."""
+    a = np.asarray(a, dtype=np.float64)
+    bad = np.isnan(a)
+    if not bad.any():
+        return a
+    o = a.astype(object)
+    o[bad] = None
+    return o
+
+
 def _show(odf, n, print_impact):
     if print_impact:
         odf.show(max(n, 1))
@@ -189,21 +201,22 @@ def measures_of_counts(spark, idf, list_of_cols="all", drop_cols=[], print_impac
     fr = as_frame(idf)
     cols = _discrete_cols(fr, list_of_cols, drop_cols)
     N = fr.count()
-    m = profile.moments(fr, [c for c in cols if fr.column(c).kind == "num"])
+    is_num = np.array([fr.column(c).kind == "num" for c in cols], dtype=bool)
+    m = profile.moments(fr, [c for c, k in zip(cols, is_num) if k])
     nv = profile.n_valid(fr, cols)       # string columns: from the code histogram when a pass already left one
-    rows = []
-    for c in cols:
-        fill = nv[c]
-        fill_pct = _R(fill / N) if N else None
-        row = [c, fill, fill_pct, N - fill, None if fill_pct is None else _R(1 - fill_pct)]
-        if fr.column(c).kind == "num":
-            nz = int(m[c]["n_nonzero"])
-            row += [nz, _R(nz / N) if N else None]
-        else:
-            row += [None, None]
-        rows.append(row)
-    odf = pd.DataFrame(rows, columns=["attribute", "fill_count", "fill_pct", "missing_count", "missing_pct",
-                                      "nonzero_count", "nonzero_pct"])
+    fill = np.array([nv[c] for c in cols], dtype=np.int64)
+    nz = np.array([int(m[c]["n_nonzero"]) if k else 0 for c, k in zip(cols, is_num)], dtype=np.int64)
+    if N:
+        fill_pct = spark_round_array(fill / N)
+        miss_pct = spark_round_array(1 - fill_pct)
+        nz_pct = spark_round_array(np.where(is_num, nz / N, np.nan))
+    else:
+        fill_pct = miss_pct = nz_pct = np.full(len(cols), np.nan)
+    nz_col = nz.astype(object)
+    nz_col[~is_num] = None
+    odf = pd.DataFrame({"attribute": cols, "fill_count": fill, "fill_pct": _opt(fill_pct), "missing_count": N - fill,
+                        "missing_pct": _opt(miss_pct), "nonzero_count": nz if is_num.all() else nz_col,
+                        "nonzero_pct": _opt(nz_pct)}, copy=False)
     return _show(ResultFrame(odf), len(cols), print_impact)
 
 
@@ -372,12 +385,13 @@ def measures_of_shape(spark, idf, list_of_cols="all", drop_cols=[], print_impact
         warnings.warn("No Skewness/Kurtosis Computation - No numerical column(s) to analyze")
         return _empty(["attribute", "skewness", "kurtosis"])
     m = profile.moments(fr, cols)
-    rows = []
-    for c in cols:
-        n, m2, m3, m4 = int(m[c]["n_valid"]), float(m[c]["m2"]), float(m[c]["m3"]), float(m[c]["m4"])
-        if n == 0 or m2 == 0:
-            rows.append([c, None, None])   # Spark >= 3.1: null when M2 == 0 (parity unpinned)
-            continue
-        rows.append([c, _R(math.sqrt(n) * m3 / math.sqrt(m2 * m2 * m2)), _R(n * m4 / (m2 * m2) - 3.0)])
-    return _show(ResultFrame(pd.DataFrame(rows, columns=["attribute", "skewness", "kurtosis"])), len(cols),
-                 print_impact)
+    n = np.array([int(m[c]["n_valid"]) for c in cols], dtype=np.float64)
+    m2 = np.array([float(m[c]["m2"]) for c in cols])
+    m3 = np.array([float(m[c]["m3"]) for c in cols])
+    m4 = np.array([float(m[c]["m4"]) for c in cols])
+    with np.errstate(all="ignore"):
+        ok = (n > 0) & (m2 != 0)                 # Spark >= 3.1: null when M2 == 0 (parity unpinned)
+        skew = spark_round_array(np.where(ok, np.sqrt(n) * m3 / np.sqrt(m2 * m2 * m2), np.nan))
+        kurt = spark_round_array(np.where(ok, n * m4 / (m2 * m2) - 3.0, np.nan))
+    odf = pd.DataFrame({"attribute": cols, "skewness": _opt(skew), "kurtosis": _opt(kurt)}, copy=False)
+    return _show(ResultFrame(odf), len(cols), print_impact)
