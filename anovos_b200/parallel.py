@@ -19,11 +19,21 @@ _NON_NUMERIC = {"attribute", "mode", "metric", "value"}
 
 
 def frames_to_matrix(frames):
-    """Result frames (pandas) -> float64 matrix [n_attributes, n_numeric_fields] + the field names.
-    Non-numeric fields (attribute, mode) stay local to the rank; they are re-attached by name."""
+    """Result frames (pandas) -> float64 matrix [n_attributes, n_numeric_fields] + the field names, aligned on
+    `attribute` (mixed frames: the numeric-only functions - dispersion, percentiles, shape - return fewer rows than the
+    functions that also cover string columns; the missing cells are NaN).  Non-numeric fields (attribute, mode) stay
+    local to the rank; they are re-attached by name."""
     import pandas as pd
+    order = {}
+    for df in frames:
+        if "attribute" in df.columns:
+            for a in df["attribute"].tolist():
+                order.setdefault(a, len(order))
+    n = len(order) if order else max((len(df) for df in frames), default=0)
     cols, names = [], []
     for df in frames:
+        rows = np.fromiter((order[a] for a in df["attribute"].tolist()), dtype=np.int64, count=len(df)) \
+            if "attribute" in df.columns else np.arange(len(df))
         for c in df.columns:
             if c in _NON_NUMERIC:
                 continue
@@ -32,7 +42,9 @@ def frames_to_matrix(frames):
                 a = a.astype(np.float64, copy=False)
             else:                       # object columns (None for "not applicable"), pandas extension arrays
                 a = pd.to_numeric(df[c], errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
-            cols.append(a)
+            full = np.full(n, np.nan)
+            full[rows] = a
+            cols.append(full)
             names.append(c)
     return np.ascontiguousarray(np.stack(cols, axis=1)), names
 

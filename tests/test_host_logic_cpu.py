@@ -99,3 +99,18 @@ def test_drift_argument_normalisers_contract():
     def g(spark, idf_target, *, cols="all", drops=None):
         return cols, drops
     assert g(None, t, cols="b|c") == (["b", "c"], [])
+
+
+def test_frames_to_matrix_aligns_frames_of_different_row_counts():
+    """Mixed frames (the default bench workload): counts / centralTendency / cardinality cover string columns, the
+    numeric-only functions do not - the summary matrix of the N > 1 exchange is aligned on `attribute`, NaN where a
+    function has no row for a column."""
+    import pandas as pd
+    from anovos_b200 import parallel
+    f1 = pd.DataFrame({"attribute": ["a", "s", "b"], "fill_count": [3, 2, 3], "mode": ["1", "x", None]})
+    f2 = pd.DataFrame({"attribute": ["a", "b"], "stddev": [0.5, None], "range": [1.0, 2.0]})
+    m, names = parallel.frames_to_matrix([f1, f2])
+    assert names == ["fill_count", "stddev", "range"] and m.shape == (3, 3)
+    assert m[:, 0].tolist() == [3.0, 2.0, 3.0]
+    assert m[0, 1] == 0.5 and np.isnan(m[1, 1]) and np.isnan(m[2, 1])
+    assert m[0, 2] == 1.0 and np.isnan(m[1, 2]) and m[2, 2] == 2.0
