@@ -32,6 +32,12 @@ def _names(x):
     return [s.strip() for s in x.split("|")] if isinstance(x, str) else list(x)
 
 
+def _require(ok, message):
+    """The reference signals every bad argument of data_sample with a TypeError (data_sampling.py:72-118)."""
+    if not ok:
+        raise TypeError(message)
+
+
 def sample_mask(n_rows: int, seed: int, thresholds, strata=None):
     """-> bool CUDA tensor [n_rows] of the rows Spark keeps in ONE partition seeded with `seed` (already seed + index).
     thresholds: ceil(fraction * 2^53) per stratum; strata: int32 CUDA tensor of stratum ids or None."""
@@ -95,14 +101,10 @@ def data_sample(idf, strata_cols="all", drop_cols=[], fraction=0.1, method_type=
                 seed_value=12, unique_threshold=0.5, partition_index=0):
     """Same arguments, checks, warnings and results as the reference (:8-149).  `partition_index` (extra): the Spark
     partition a ColumnFrame stands for (default 0 - a frame is one partition)."""
-    if type(fraction) != float and type(fraction) != int:
-        raise TypeError("Invalid input for fraction")
-    if fraction <= 0 or fraction > 1:
-        raise TypeError("Invalid input for fraction: fraction value is between 0 and 1")
-    if type(seed_value) != int:
-        raise TypeError("Invalid input for seed_value")
-    if method_type not in ["stratified", "random"]:
-        raise TypeError("Invalid input for data_sample method_type")
+    _require(type(fraction) in (float, int), "Invalid input for fraction")
+    _require(0 < fraction <= 1, "Invalid input for fraction: fraction value is between 0 and 1")
+    _require(type(seed_value) is int, "Invalid input for seed_value")
+    _require(method_type in ("stratified", "random"), "Invalid input for data_sample method_type")
     fr = as_frame(idf)
     if getattr(fr, "is_partitioned", False):
         return _sample_partitions(fr, strata_cols, drop_cols, fraction, method_type, stratified_type, seed_value, unique_threshold)
@@ -115,25 +117,20 @@ def data_sample(idf, strata_cols="all", drop_cols=[], fraction=0.1, method_type=
 
 
 def _checked_strata(fr, strata_cols, drop_cols, stratified_type, unique_threshold):
-    if type(unique_threshold) != float and type(unique_threshold) != int:
-        raise TypeError("Invalid input for unique_threshold")
-    if unique_threshold > 1 and type(unique_threshold) != int:
-        raise TypeError("Invalid input for unique_threshold: unique_threshold can only be integer if larger than 1")
-    if unique_threshold <= 0:
-        raise TypeError("Invalid input for unique_threshold: unique_threshold value is either between 0 and 1, or an integer > 1")
-    if stratified_type not in ["population", "balanced"]:
-        raise TypeError("Invalid input for stratified_type")
+    _require(type(unique_threshold) in (float, int), "Invalid input for unique_threshold")
+    _require(unique_threshold <= 1 or type(unique_threshold) is int,
+             "Invalid input for unique_threshold: unique_threshold can only be integer if larger than 1")
+    _require(unique_threshold > 0,
+             "Invalid input for unique_threshold: unique_threshold value is either between 0 and 1, or an integer > 1")
+    _require(stratified_type in ("population", "balanced"), "Invalid input for stratified_type")
     if isinstance(strata_cols, str) and strata_cols == "all":
         strata_cols = fr.columns
     strata_cols, drop_cols = _names(strata_cols), _names(drop_cols)
     strata_cols = list(dict.fromkeys(e for e in strata_cols if e not in drop_cols))
-    if len(strata_cols) == 0:
-        raise TypeError("Missing strata_cols value")
+    _require(strata_cols, "Missing strata_cols value")
     for col in strata_cols:
-        if col not in fr.columns:
-            raise TypeError("Invalid input for strata_cols: " + col + " does not exist")
-        if fr.column(col).kind == "other":
-            raise TypeError("Invalid input for strata_cols: dtype of %s is not numerical/categorical" % col)
+        _require(col in fr.columns, "Invalid input for strata_cols: " + col + " does not exist")
+        _require(fr.column(col).kind != "other", "Invalid input for strata_cols: dtype of %s is not numerical/categorical" % col)
     # `select(col).distinct().count()` counts the null group as one value; `select(col).count()` is the row count
     md = profile.mode_distinct(fr, strata_cols)
     nv = profile.n_valid(fr, strata_cols)
