@@ -122,8 +122,15 @@ template <typename K> struct SortParams {
 };
 constexpr int PACK_TPC = 8;     // tiles per pack CTA (amortises the flush of the digit histograms)
 
-template <typename K> __device__ __forceinline__ uint32_t digit_of(K k, int pass) {
-  return (uint32_t)(k >> (pass * 8)) & 0xFFu;
+// byte `pass` of the key: ONE PRMT (selector nibble 0 = the byte, the other result bytes come from the zero operand)
+// instead of a shift and a mask - the digit is extracted three times per key and pass in the scatter.
+template <typename K> __device__ __forceinline__ uint32_t digit_of(K k, int pass);
+template <> __device__ __forceinline__ uint32_t digit_of<uint32_t>(uint32_t k, int pass) {
+  return __byte_perm(k, 0u, 0x4440u | (uint32_t)pass);
+}
+template <> __device__ __forceinline__ uint32_t digit_of<uint64_t>(uint64_t k, int pass) {
+  const uint32_t half = (pass & 4) ? (uint32_t)(k >> 32) : (uint32_t)k;
+  return __byte_perm(half, 0u, 0x4440u | (uint32_t)(pass & 3));
 }
 
 // ---- pack: values -> keys, nulls dropped --------------------------------------------------
@@ -709,11 +716,12 @@ __global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K>
   const int hp = P.hll_p;
   if (hp) {
     // The run heads are first COMPACTED into shared memory (a thread holds between 1 and 16 of them: hashing in place would
-    // keep every warp busy for the maximum over its lanes), then hashed by full warps.
-    const int hm = 1 << hp;
-    K* hk = reinterpret_cast<K*>(hll_sh + hm);                 // [SORT_TILE] head keys
+    // keep every warp busy for the maximum over its lanes), then hashed by full warps straight against the column's global
+    // registers: 2^p words that live in L1 / L2, read before the (rare) atomicMax.  A stale cached register can only be too
+    // LOW (registers never decrease), which costs a redundant atomic, never a wrong result - so there is no per-tile copy
+    // of the registers to clear and merge.
+    K* hk = reinterpret_cast<K*>(hll_sh);                      // [SORT_TILE] head keys
     __shared__ uint32_t s_hw[ANV_WARPS + 1];
-    for (int i = tid; i < hm; i += ANV_BLOCK) hll_sh[i] = 0;
     uint32_t hcnt = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) hcnt += (j < m && (j == 0 || k[j] != k[j - 1])) ? 1u : 0u;
@@ -735,16 +743,11 @@ __global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K>
     __syncthreads();
     const uint32_t n_heads = s_hw[ANV_WARPS];
     const int dt = P.cols[c].dtype;
+    uint32_t* G = P.hll_regs + ((size_t)c << hp);
     for (uint32_t i = tid; i < n_heads; i += ANV_BLOCK) {
       uint32_t idx, rho;
       hll_slot(spark_hash_of_key<K>(hk[i], dt), hp, idx, rho);
-      if (rho > hll_sh[idx]) atomicMax(&hll_sh[idx], rho);
-    }
-    __syncthreads();
-    uint32_t* G = P.hll_regs + ((size_t)c << hp);
-    for (int i = tid; i < hm; i += ANV_BLOCK) {
-      const uint32_t v = hll_sh[i];
-      if (v && v > G[i]) atomicMax(&G[i], v);       // the registers saturate after a few tiles: almost no atomics later
+      if (rho > G[idx]) atomicMax(&G[idx], rho);
     }
   }
 #pragma unroll
@@ -938,9 +941,7 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
         ANV_CUDA(cudaGetLastError());
       }
     }
-    const size_t run_smem = P.hll_p ? ((size_t)4 << P.hll_p) + (size_t)SORT_TILE * sizeof(K) : 0;   // registers + head keys
-    if (run_smem > 40 * 1024)    // dynamic + the kernel's static shared memory must stay under the default 48 KB otherwise
-      ANV_CUDA(cudaFuncSetAttribute(run_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run_smem));
+    const size_t run_smem = P.hll_p ? (size_t)SORT_TILE * sizeof(K) : 0;   // the compacted head keys
     run_tile_kernel<K><<<grid, ANV_BLOCK, run_smem, st>>>(P);
     ANV_CUDA(cudaGetLastError());
   }
