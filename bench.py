@@ -388,6 +388,7 @@ def rowslab_check(rank, world, torch, dist):
     a = dd.statistics(None, twhole, whole, source_path=tempfile.mkdtemp(), **kw).toPandas()
     b = dd.statistics(None, tparts, parts, source_path=tempfile.mkdtemp(), **kw).toPandas()
     ok &= all(np.allclose(a[m], b[m], rtol=1e-9, atol=0) for m in ("PSI", "HD", "JSD", "KS")) and list(a["flagged"]) == list(b["flagged"])
+    repartition_to_columns(slab, True)      # first exchange: NCCL sets up the point-to-point connections (seconds at 8 ranks)
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
