@@ -42,15 +42,9 @@ def _empty(cols):
 
 
 def _opt(a):
-    """float64 array with NaN = null -> column for a result frame: stays float64 when nothing is null, else object with None
-    (what the row-wise construction produced: the reference frames hold nulls, not NaNs)."""
-    a = np.asarray(a, dtype=np.float64)
-    bad = np.isnan(a)
-    if not bad.any():
-        return a
-    o = a.astype(object)
-    o[bad] = None
-    return o
+    """float64 column of a result frame, NaN = null: what pandas infers from a row-wise list holding None (the dtype the
+    frames have always had; `pd.isna` is the null test either way)."""
+    return np.asarray(a, dtype=np.float64)
 
 
 def _show(odf, n, print_impact):
@@ -212,11 +206,9 @@ def measures_of_counts(spark, idf, list_of_cols="all", drop_cols=[], print_impac
         nz_pct = spark_round_array(np.where(is_num, nz / N, np.nan))
     else:
         fill_pct = miss_pct = nz_pct = np.full(len(cols), np.nan)
-    nz_col = nz.astype(object)
-    nz_col[~is_num] = None
+    nz_col = nz if is_num.all() else np.where(is_num, nz.astype(np.float64), np.nan)   # string columns: null
     odf = pd.DataFrame({"attribute": cols, "fill_count": fill, "fill_pct": _opt(fill_pct), "missing_count": N - fill,
-                        "missing_pct": _opt(miss_pct), "nonzero_count": nz if is_num.all() else nz_col,
-                        "nonzero_pct": _opt(nz_pct)}, copy=False)
+                        "missing_pct": _opt(miss_pct), "nonzero_count": nz_col, "nonzero_pct": _opt(nz_pct)}, copy=False)
     return _show(ResultFrame(odf), len(cols), print_impact)
 
 
