@@ -675,9 +675,10 @@ template <typename K> __device__ __forceinline__ TileSummary<K> shfl_down_summar
 // Each thread summarises 16 CONSECUTIVE sorted keys in registers (blocked 128-bit loads), the 256
 // thread summaries are folded with the associative `combine` (shuffle tree per warp, then 8 warps
 // sequentially): no shared-memory tile, no binary search, ~25 instructions per key.
+constexpr int RUN_TPC = 4;      // tiles per run-summary CTA
 template <typename K>
-__global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K> P) {
-  const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void run_tile_one(const SortParams<K>& P, const int c, const int tile) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ColState& S = P.state[c];
   const int64_t n = (int64_t)S.n_valid;
   const int64_t t0 = (int64_t)tile * SORT_TILE;
@@ -775,6 +776,16 @@ __global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K>
 #pragma unroll
     for (int w = 1; w < ANV_WARPS; ++w) acc = combine(acc, ws[w]);
     out = acc;
+  }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(ANV_BLOCK) run_tile_kernel(const SortParams<K> P) {
+  for (int tt = 0; tt < RUN_TPC; ++tt) {
+    const int tile = blockIdx.x * RUN_TPC + tt;
+    if (tile >= P.n_tiles) return;
+    run_tile_one<K>(P, blockIdx.y, tile);
+    __syncthreads();           // the shared staging (head keys, warp summaries) is reused by the next tile
   }
 }
 
@@ -954,7 +965,7 @@ static int run_mode_distinct(const anv_column_t* cols, int n_cols, int64_t n_row
       }
     }
     const size_t run_smem = P.hll_p ? (size_t)SORT_TILE * sizeof(K) : 0;   // the compacted head keys
-    run_tile_kernel<K><<<grid, ANV_BLOCK, run_smem, st>>>(P);
+    run_tile_kernel<K><<<dim3((P.n_tiles + RUN_TPC - 1) / RUN_TPC, n_cols), ANV_BLOCK, run_smem, st>>>(P);
     ANV_CUDA(cudaGetLastError());
   }
   run_merge_kernel<K><<<n_cols, 32 * MERGE_WARPS, 0, st>>>(P, mode_value, mode_rows, n_distinct, ranks, n_ranks, rank_values);
