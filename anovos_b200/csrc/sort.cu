@@ -319,7 +319,10 @@ __device__ __forceinline__ uint32_t peers8(uint32_t d, uint32_t act) {
 // ---- pass step 1: per-tile digit histogram ------------------------------------------------------
 // Plain shared-memory atomics (hardware handles same-address lanes far faster than a
 // match_any pre-aggregation: measured 4-5x on B200).
-constexpr int HIST_TPC = 4;   // tiles per CTA: the two dependent loads that start a CTA (column state, then keys) are paid once per 64 KB
+#ifndef ANV_HIST_TPC
+#define ANV_HIST_TPC 1
+#endif
+constexpr int HIST_TPC = ANV_HIST_TPC;   // tiles per tile-histogram CTA (tuning knob; measured: see DESIGN.md section 3)
 template <typename K>
 __global__ void __launch_bounds__(ANV_BLOCK) sort_hist_kernel(const SortParams<K> P) {
   const int c = blockIdx.y, tid = threadIdx.x;
@@ -589,7 +592,10 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
   }
 }
 
-constexpr int SCAT_TPC = 2;     // tiles per scatter CTA: the column-state / tile-offset loads that start a tile overlap the previous tile's copy-out
+#ifndef ANV_SCAT_TPC
+#define ANV_SCAT_TPC 1
+#endif
+constexpr int SCAT_TPC = ANV_SCAT_TPC;   // tiles per scatter CTA (tuning knob)
 template <typename K>
 __global__ void __launch_bounds__(SCAT_THREADS, ANV_SCAT_MINB) sort_scatter_kernel(const SortParams<K> P) {
   const int c = blockIdx.y;
@@ -675,7 +681,10 @@ template <typename K> __device__ __forceinline__ TileSummary<K> shfl_down_summar
 // Each thread summarises 16 CONSECUTIVE sorted keys in registers (blocked 128-bit loads), the 256
 // thread summaries are folded with the associative `combine` (shuffle tree per warp, then 8 warps
 // sequentially): no shared-memory tile, no binary search, ~25 instructions per key.
-constexpr int RUN_TPC = 4;      // tiles per run-summary CTA
+#ifndef ANV_RUN_TPC
+#define ANV_RUN_TPC 1
+#endif
+constexpr int RUN_TPC = ANV_RUN_TPC;     // tiles per run-summary CTA (tuning knob)
 template <typename K>
 __device__ __forceinline__ void run_tile_one(const SortParams<K>& P, const int c, const int tile) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
