@@ -320,9 +320,12 @@ __device__ __forceinline__ uint32_t peers8(uint32_t d, uint32_t act) {
 // Plain shared-memory atomics (hardware handles same-address lanes far faster than a
 // match_any pre-aggregation: measured 4-5x on B200).
 #ifndef ANV_HIST_TPC
-#define ANV_HIST_TPC 1
+#define ANV_HIST_TPC 4
 #endif
-constexpr int HIST_TPC = ANV_HIST_TPC;   // tiles per tile-histogram CTA (tuning knob; measured: see DESIGN.md section 3)
+// tiles per tile-histogram CTA.  Measured (c2 / c3 sort call, ms): 1 tile 11.36 / 317.3, 4 tiles 11.19 / 314.8 - the two dependent
+// loads that start a CTA (column state, then keys) are paid once per 64 KB.  The same knob on the scatter (2 tiles: 12.42 /
+// 354.6) and the run summaries (4 tiles: 11.29 / 316.8) does not pay and stays at 1.
+constexpr int HIST_TPC = ANV_HIST_TPC;
 template <typename K>
 __global__ void __launch_bounds__(ANV_BLOCK) sort_hist_kernel(const SortParams<K> P) {
   const int c = blockIdx.y, tid = threadIdx.x;
