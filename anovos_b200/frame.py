@@ -21,6 +21,21 @@ _NUMERIC_SPARK = ("double", "int", "bigint", "float", "long")
 
 h2d_bytes = 0  # bytes uploaded to the device by Column.device()
 
+_SIDE_STREAMS = {}
+
+
+def side_stream():
+    """ONE side stream per device for asynchronous uploads / chunk generation.  torch's caching allocator keeps a pool per
+    stream: a fresh stream per pass would cudaMalloc every chunk again (measured: the streamed c4 step went from 0.36 s to 1.3 s)."""
+    torch = _lib.require_cuda()
+    if not hasattr(torch.cuda, "current_device"):      # the CPU engine stand-in of the tests: no streams
+        return torch.cuda.Stream()
+    dev = torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(dev)
+    if st is None:
+        st = _SIDE_STREAMS[dev] = torch.cuda.Stream()
+    return st
+
 
 def spark_dtype_of_arrow(t) -> str:
     """Arrow type -> Spark SQL dtype string as `idf.dtypes` would print it."""

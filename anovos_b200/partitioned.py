@@ -106,6 +106,12 @@ class _Group:
         return [o.cpu().numpy().view(rec.dtype) for o in out]
 
 
+def _side_stream():
+    """The device's persistent side stream (frame.side_stream); the CPU engine stand-in of the tests has no streams."""
+    from . import frame as _frame
+    return _frame.side_stream()
+
+
 class PartitionedFrame:
     """Frame-like object over row partitions.  `schema` is a ColumnFrame (any row count, usually
     the first chunk or an empty frame) that supplies column names, dtypes and dictionaries;
@@ -237,13 +243,13 @@ class PartitionedFrame:
                         continue
                     if c._host is not None:
                         if copy is None:
-                            copy = torch.cuda.Stream()
+                            copy = _side_stream()
                         c.upload_async(copy)
                     elif c._loader is not None:
                         # generated chunks (synthetic frames): run the generator of chunk i+1 on the side stream while the
                         # scan kernels of chunk i run - the generator is ALU-bound, the scans HBM-bound
                         if copy is None:
-                            copy = torch.cuda.Stream()
+                            copy = _side_stream()
                         c.generate_async(copy)
             yield cur
             if self._release:

@@ -165,7 +165,8 @@ def prefetch(frame: ColumnFrame, names=None, want=("moments", "mode", "hll"), rs
         return frame  # chunks are uploaded (and freed) pass by pass
     torch = _lib.require_cuda()
     names = [n for n in (names or frame.columns) if frame.column(n).kind != "other"]
-    copy = torch.cuda.Stream()
+    from .frame import side_stream
+    copy = side_stream()
     for n in names:
         frame.column(n).upload_async(copy)
     for g0 in range(0, len(names), group):
