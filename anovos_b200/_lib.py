@@ -62,6 +62,7 @@ _SIGNATURES = {
     "anv_select_advance": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "anv_hll_registers": (C.c_int, [_P, _I, _L, _I, _P, _P]),
     "anv_xxh64_utf8": (C.c_int, [_P, _P, _L, _P]),
+    "anv_gk_partition_sketch": (C.c_longlong, [_P, C.c_longlong, C.c_longlong, C.c_double, C.c_longlong, _P, _P, _P, C.c_longlong]),
     "anv_mode_distinct_workspace_bytes": (_SZ, [_I, _L, _I]),
     "anv_mode_distinct": (C.c_int, [_P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "anv_mode_distinct_hll": (C.c_int, [_P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _SZ, _P]),

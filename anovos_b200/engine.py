@@ -334,7 +334,8 @@ def quantile_ranks(n_valid: int, probs, eps=None):
     """1-based ranks of the order statistics Spark returns for `probs` over n_valid non-null values.
     eps None: the exact rule max(1, ceil(p * n)) with p * n in float64.  eps = the relativeError of
     the Spark call being replaced (1e-4 for summary(), 0.01 for approxQuantile): the Greenwald-Khanna sketch
-    position for one partition of < 50 000 values, the exact rule beyond (shared/gk.py)."""
+    position for one partition of < 50 000 values, the exact rule beyond (shared/gk.py; frames tagged with their
+    Spark partitioning go through PartitionedFrame.gk_quantiles instead, any partition size)."""
     return _gk.spark_ranks(int(n_valid), probs, eps)
 
 

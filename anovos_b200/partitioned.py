@@ -369,10 +369,11 @@ class PartitionedFrame:
     def gk_quantiles(self, names, probs, eps):
         """Spark-partitioned frames (`spark_partitions=True`: every chunk is one Spark partition, in order): the
         quantiles Dataset.summary() / approxQuantile return - one Greenwald-Khanna sketch per partition, merged in
-        partition order (shared/gk.py).  The sketch keeps the order statistics at data-independent positions, so the
-        sort kernel supplies them per partition and only those few thousand samples are merged on the host.
-        -> dict name -> [value | None per prob], or None when a partition holds >= 50 000 non-null values of some
-        column (Spark then flushes its head buffer mid-partition: arrival-order dependent, not emulated)."""
+        partition order (shared/gk.py).  A partition of fewer than 50 000 non-null values keeps the order statistics at
+        data-independent positions, so the sort kernel supplies just those few thousand samples.  A LARGER partition makes
+        Spark flush its 50 000-value head buffer as the rows arrive: every batch of 50 000 consecutive non-null values is
+        sorted on the device (one "column" per batch) and the strictly sequential merge / compress runs in the library's
+        host helper (anv_gk_partition_sketch).  -> dict name -> [value | None per prob]."""
         from . import engine
         from .shared import gk
         names = [n for n in names]
@@ -380,19 +381,23 @@ class PartitionedFrame:
         for ch in self.chunks(names):
             mom = engine.moments(ch, names)
             nv = [int(m["n_valid"]) for m in mom]
-            if any(k >= gk.HEAD_SIZE for k in nv):
-                return None
-            pos = [gk.sample_positions(k, eps) for k in nv]
-            width = max((len(q) for q in pos), default=0)
-            if width == 0:
-                continue
-            rk = np.zeros((len(names), width), np.int64)
-            for i, q in enumerate(pos):
-                rk[i, :len(q)] = q + 1
-            _, vals = engine.sort_mode_distinct(ch, names, rk)
-            for i, n in enumerate(names):
-                s = gk.partition_samples(vals[i, :len(pos[i])], nv[i], eps)
-                sketch[n] = gk.merge_samples(sketch[n][0], sketch[n][1], s, nv[i], eps)
+            small = [i for i, k in enumerate(nv) if k < gk.HEAD_SIZE]
+            if small:
+                sub = [names[i] for i in small]
+                pos = [gk.sample_positions(nv[i], eps) for i in small]
+                width = max((len(q) for q in pos), default=0)
+                if width:
+                    rk = np.zeros((len(sub), width), np.int64)
+                    for j, q in enumerate(pos):
+                        rk[j, :len(q)] = q + 1
+                    _, vals = engine.sort_mode_distinct(ch, sub, rk)
+                    for j, i in enumerate(small):
+                        s = gk.partition_samples(vals[j, :len(pos[j])], nv[i], eps)
+                        sketch[names[i]] = gk.merge_samples(sketch[names[i]][0], sketch[names[i]][1], s, nv[i], eps)
+            for i, k in enumerate(nv):
+                if k >= gk.HEAD_SIZE:
+                    s = _large_partition_sketch(ch, names[i], k, eps)
+                    sketch[names[i]] = gk.merge_samples(sketch[names[i]][0], sketch[names[i]][1], s, k, eps)
         return {n: [gk.query_samples(sketch[n][0], sketch[n][1], eps, p) for p in probs] for n in names}
 
     def materialize(self, names=None) -> ColumnFrame:
@@ -460,6 +465,42 @@ class PartitionedFrame:
 
 
 # ---- row slabs -> column blocks (the one real exchange step) ---------------------------------------
+
+def _large_partition_sketch(ch: ColumnFrame, name: str, n_valid: int, eps: float, batches_per_call: int = 128):
+    """Spark's sketch of ONE partition with >= 50 000 non-null values of column `name` -> [(value, g, delta)].
+    Device: the non-null values in arrival order, cut into head-buffer batches of 50 000; each batch goes through the
+    radix sort as one column and comes back fully ordered through its rank outputs.  Host: anv_gk_partition_sketch."""
+    import ctypes as C
+    from . import engine
+    from .shared import gk
+    L = _lib.lib()
+    H = gk.HEAD_SIZE
+    d, v = ch.column(name).device()
+    vals = d if v is None else d[ch.valid_mask(name)]          # arrival order, nulls dropped (a gather: plumbing)
+    n = int(vals.shape[0])
+    assert n == n_valid, (n, n_valid)
+    parts = []
+    nb, rem = n // H, n % H
+    full_ranks = np.arange(1, H + 1, dtype=np.int64)
+    for b0 in range(0, nb, batches_per_call):
+        b1 = min(nb, b0 + batches_per_call)
+        cols = {"b%06d" % j: vals[j * H:(j + 1) * H] for j in range(b0, b1)}
+        bf = ColumnFrame.from_tensors(cols, n_rows=H)
+        _, sv = engine.sort_mode_distinct(bf, list(cols), np.tile(full_ranks, (b1 - b0, 1)))
+        parts.append(np.ascontiguousarray(sv, dtype=np.float64).reshape(-1))
+    if rem:
+        bf = ColumnFrame.from_tensors({"rest": vals[nb * H:]}, n_rows=rem)
+        _, sv = engine.sort_mode_distinct(bf, ["rest"], np.arange(1, rem + 1, dtype=np.int64).reshape(1, -1))
+        parts.append(np.ascontiguousarray(sv, dtype=np.float64).reshape(-1))
+    sb = np.concatenate(parts) if parts else np.zeros(0)
+    cap = n + 8
+    ov, og, od = np.zeros(cap), np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+    k = L.anv_gk_partition_sketch(sb.ctypes.data_as(C.c_void_p), n, H, float(eps), gk.COMPRESS_THRESHOLD, ov.ctypes.data_as(C.c_void_p),
+                                  og.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), cap)
+    if k < 0:
+        _lib.check(int(k), "anv_gk_partition_sketch")
+    return list(zip(ov[:k].tolist(), og[:k].tolist(), od[:k].tolist()))
+
 
 def repartition_to_columns(frame: ColumnFrame, group=True, names=None) -> ColumnFrame:
     """All-to-all over the group (NCCL over NVLink on GPUs): every rank holds a row slab of ALL

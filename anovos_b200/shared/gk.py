@@ -28,6 +28,7 @@ import math
 import numpy as np
 
 HEAD_SIZE = 50000          # QuantileSummaries.defaultHeadSize
+COMPRESS_THRESHOLD = 10000  # QuantileSummaries.defaultCompressThreshold
 SUMMARY_EPS = 1e-4         # Dataset.summary(): ApproximatePercentile, accuracy 10000
 APPROX_QUANTILE_EPS = 0.01  # the relativeError of every approxQuantile call on the path
 

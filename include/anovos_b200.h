@@ -175,6 +175,15 @@ int anv_hll_registers(const anv_column_t* cols, int n_cols, int64_t n_rows, int 
  * string columns.  bytes/offsets/out are HOST pointers. */
 int anv_xxh64_utf8(const uint8_t* bytes, const int64_t* offsets, int64_t n, uint64_t* out);
 
+/* Host helper for partitions LARGER than Spark's 50 000-value head buffer (QuantileSummaries.insert flushes the buffer every
+ * head_size insertions and compresses at >= compress_threshold samples; the final compress() inserts the rest): the caller
+ * sorts every batch of head_size consecutive non-null values on the device (anv_mode_distinct with all ranks requested) and
+ * passes them concatenated, each batch ascending.  Strictly sequential merge / compress, ~2 steps per value.  HOST pointers.
+ * Returns the number of samples written to (out_value, out_g, out_delta), or a negative anv_status. */
+long long anv_gk_partition_sketch(const double* sorted_batches, long long n_values, long long head_size, double eps,
+                                  long long compress_threshold, double* out_value, long long* out_g, long long* out_delta,
+                                  long long capacity);
+
 /* ---- exact mode / distinct count of numeric columns (mode_computation's per-column
  *      groupBy+sort jobs, stats_generator.py:386-401; countDistinct, :611): batched LSD
  *      radix sort of the non-null values' order-preserving keys + run-length summary.

@@ -644,3 +644,18 @@ def test_nb_attribute_binning_head(tr, income_spark):
         got = [[int(first.column(c).device()[0][i].item()) for c in ("education-num", "hours-per-week")] for i in range(5)]
         assert got == exp, (method, got)
 
+
+
+def test_percentiles_of_partitions_beyond_the_head_buffer(sg):
+    """Spark partitions of >= 50 000 non-null values: the device sorts every 50 000-value head-buffer batch, the library's
+    host helper runs Spark's sequential merge / compress -> product == the oracle's sketch on every percentile, median,
+    IQR; float64 with nulls, float32, int32 and a mostly-null column that stays under the head size."""
+    from test_host_paths_cpu import _large_partition_table
+    t, parts = _large_partition_table()
+    tt = O.with_spark_partitions(t, parts)
+    got = sg.measures_of_percentiles(None, tt).toPandas()
+    exp = O.measures_of_percentiles(tt)
+    assert got.equals(exp), (got, exp)
+    assert sg.measures_of_dispersion(None, tt).toPandas()["IQR"].tolist() == O.measures_of_dispersion(tt)["IQR"].tolist()
+    assert sg.measures_of_centralTendency(None, tt).toPandas()["median"].tolist() == O.measures_of_centralTendency(tt)["median"].tolist()
+    assert not O.measures_of_percentiles(t).equals(exp)

@@ -297,3 +297,53 @@ def test_outlier_nan_values_are_not_outliers(tmp_path):
     assert base.loc["x", "upper_outliers"] + 5 - clean_upper_in_first12 <= r.loc["x", "upper_outliers"] <= base.loc["x", "upper_outliers"] + 5
     valid = np.unpackbits(v.numpy().view(np.uint8), bitorder="little")[:4000].astype(bool)
     assert valid[:7].all() and not valid[7:12].any()             # NaNs stay, the five 50.0s became null
+
+
+def _large_partition_table():
+    rng = np.random.default_rng(3)
+    n = 260_000
+    t = pa.table({"x": pa.array(np.round(rng.normal(10, 50, n), 1), mask=rng.random(n) < 0.05),
+                  "f": pa.array(rng.lognormal(0, 1, n).astype(np.float32)),
+                  "i": pa.array(rng.integers(0, 1000, n).astype(np.int32)),
+                  "mostly_null": pa.array(rng.normal(0, 1, n), mask=rng.random(n) < 0.9)})
+    return t, [120_001, 49_999, 60_000, 30_000]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 777, 49_999, 50_000, 50_001, 120_001, 260_007])
+@pytest.mark.parametrize("eps", [1e-4, 0.01])
+def test_gk_partition_sketch_helper_equals_oracle(n, eps):
+    """anv_gk_partition_sketch (host helper of the C ABI: Spark's head-buffer flush + compress over batches the device has
+    sorted) returns the oracle's sketch of the same arrival-ordered values, sample for sample."""
+    import ctypes as C
+    from anovos_b200 import _lib
+    L = _lib.lib()
+    v = np.round(np.random.default_rng(n).normal(0, 100, n), 1)
+    H = 50_000
+    sb = np.concatenate([np.sort(v[i:i + H]) for i in range(0, n, H)]) if n else np.zeros(0)
+    cap = n + 8
+    ov, og, od = np.zeros(cap), np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+    k = L.anv_gk_partition_sketch(sb.ctypes.data_as(C.c_void_p), n, H, eps, 10_000, ov.ctypes.data_as(C.c_void_p),
+                                  og.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), cap)
+    exp, cnt = S.gk_sketch(v, eps)
+    assert cnt == n and k == len(exp)
+    assert [(a, int(b), int(c)) for a, b, c in zip(ov[:k], og[:k], od[:k])] == [(float(a), int(b), int(c)) for a, b, c in exp]
+    if n > 4:      # capacity too small: error code, nothing written past the end
+        assert L.anv_gk_partition_sketch(sb.ctypes.data_as(C.c_void_p), n, H, eps, 10_000, ov.ctypes.data_as(C.c_void_p),
+                                         og.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), 2) < 0
+
+
+def test_percentiles_of_partitions_beyond_the_head_buffer_host_path():
+    """Partitions of >= 50 000 non-null values (Spark flushes its head buffer as rows arrive): product == the oracle's
+    sketch for every percentile, the median and the IQR; and the result is NOT the exact order statistic everywhere."""
+    import anovos.data_analyzer.stats_generator as sg
+    t, parts = _large_partition_table()
+    tt = O.with_spark_partitions(t, parts)
+    with cpu_engine.installed():
+        got = sg.measures_of_percentiles(None, tt).toPandas()
+        disp = sg.measures_of_dispersion(None, tt).toPandas()
+        cen = sg.measures_of_centralTendency(None, tt).toPandas()
+    exp = O.measures_of_percentiles(tt)
+    assert got.equals(exp)
+    assert disp["IQR"].tolist() == O.measures_of_dispersion(tt)["IQR"].tolist()
+    assert cen["median"].tolist() == O.measures_of_centralTendency(tt)["median"].tolist()
+    assert not O.measures_of_percentiles(t).equals(exp)
