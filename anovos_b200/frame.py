@@ -120,6 +120,25 @@ def _arrow_validity_words(arr):
     return _pack_validity(np.asarray(arr.is_valid()))
 
 
+def narrow_code_dtype(cardinality: int):
+    """Host storage type of the dictionary codes of a string column: the narrowest of uint8 / int16 / int32 that holds
+    every code (the way Parquet and Arrow keep dictionary indices).  Fewer bytes cross PCIe; the device copy is widened to
+    the int32 the kernels read right after the upload, on the upload's stream."""
+    if cardinality <= 256:
+        return np.uint8
+    if cardinality <= 32768:
+        return np.int16
+    return np.int32
+
+
+def narrow_codes(codes: np.ndarray, cardinality: int) -> np.ndarray:
+    dt = narrow_code_dtype(cardinality)
+    return codes if codes.dtype == dt else codes.astype(dt)
+
+
+_CODE_DTYPES = (np.dtype(np.uint8), np.dtype(np.int16), np.dtype(np.int32))
+
+
 class Column:
     __slots__ = ("name", "sdtype", "kind", "anv_dtype", "n_rows", "null_count", "dictionary",
                  "_host", "_host_valid", "_dev", "_dev_valid", "_ready", "_loader")
@@ -152,6 +171,8 @@ class Column:
             dev = torch.empty(th.shape, dtype=th.dtype, device="cuda")
             dev.copy_(th, non_blocking=True)
             h2d_bytes += h.nbytes
+            if self.dictionary is not None and dev.dtype != torch.int32:
+                dev = dev.to(torch.int32)      # narrow host codes -> the int32 codes the kernels read
             if self._host_valid is not None:
                 tv = torch.from_numpy(self._host_valid)
                 dv = torch.empty(tv.shape, dtype=tv.dtype, device="cuda")
@@ -203,6 +224,8 @@ class Column:
             # pinned host buffers upload asynchronously on the current stream (stream-ordered with the kernels)
             self._dev = t.cuda(non_blocking=t.is_pinned())
             h2d_bytes += h.nbytes
+            if self.dictionary is not None and self._dev.dtype != torch.int32:
+                self._dev = self._dev.to(torch.int32)
             if self._host_valid is not None:
                 tv = torch.from_numpy(self._host_valid)
                 self._dev_valid = tv.cuda(non_blocking=tv.is_pinned())
@@ -338,7 +361,7 @@ class ColumnFrame:
                 bits = np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:self.n_rows]
                 mask = bits == 0
             if c.dictionary is not None:
-                idx = pa.array(vals[:self.n_rows], type=pa.int32(), mask=mask)
+                idx = pa.array(np.asarray(vals[:self.n_rows]).astype(np.int32, copy=False), type=pa.int32(), mask=mask)
                 arrays.append(pa.DictionaryArray.from_arrays(idx, pa.array(c.dictionary, type=pa.string())).cast(pa.string()))
             else:
                 arrays.append(pa.array(vals[:self.n_rows], mask=mask))
@@ -375,7 +398,7 @@ class ColumnFrame:
                 remap = np.empty(max(len(dic), 1), dtype=np.int32)
                 remap[np.asarray(order, dtype=np.int64)] = np.arange(len(dic), dtype=np.int32)
                 codes = remap[codes] if len(dic) else codes
-                cols[field.name] = Column(field.name, "string", n, host=np.ascontiguousarray(codes),
+                cols[field.name] = Column(field.name, "string", n, host=np.ascontiguousarray(narrow_codes(codes, len(dic))),
                                           host_valid=_arrow_validity_words(idx), anv_dtype=_lib.ANV_I32,
                                           null_count=idx.null_count, dictionary=[dic[i] for i in order])
                 continue
@@ -398,7 +421,8 @@ class ColumnFrame:
     @staticmethod
     def from_tensors(data: dict, n_rows=None) -> "ColumnFrame":
         """dict name -> tensor | (tensor, validity_words) | (codes, validity_words, dictionary).
-        Tensors may be torch (CUDA or CPU) or numpy; dtype float32/float64/int32/int64.
+        Tensors may be torch (CUDA or CPU) or numpy; dtype float32/float64/int32/int64; HOST dictionary codes may also be
+        uint8 / int16 (narrow_code_dtype).
         validity_words: int32 Arrow bitmap words (ceil(n/32)) or None."""
         import torch
         cols = OrderedDict()
@@ -412,9 +436,12 @@ class ColumnFrame:
                     v, valid = v
             is_torch = isinstance(v, torch.Tensor)
             npdt = np.dtype(str(v.dtype).replace("torch.", "")) if is_torch else np.asarray(v).dtype
-            if npdt not in _NP_TO_ANV:
+            if dic is not None and npdt in _CODE_DTYPES and not (is_torch and v.is_cuda):
+                anv_dt, sd = _lib.ANV_I32, "string"     # host codes may be narrow (narrow_code_dtype): widened on upload
+            elif npdt not in _NP_TO_ANV:
                 raise TypeError("column %r: unsupported dtype %s" % (name, npdt))
-            anv_dt, sd = _NP_TO_ANV[npdt]
+            else:
+                anv_dt, sd = _NP_TO_ANV[npdt]
             n = int(v.shape[0])
             if n_rows is None:
                 n_rows = n
@@ -423,7 +450,7 @@ class ColumnFrame:
             if dic is not None:
                 sd = "string"
                 if anv_dt != _lib.ANV_I32:
-                    raise TypeError("dictionary codes must be int32")
+                    raise TypeError("dictionary codes must be int32 (uint8 / int16 are accepted for host buffers)")
             if is_torch and v.is_cuda:
                 if v.data_ptr() % 16 or not v.is_contiguous():
                     v = v.contiguous().clone()

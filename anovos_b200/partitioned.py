@@ -542,7 +542,8 @@ def repartition_to_columns(frame: ColumnFrame, group=True, names=None) -> Column
         if c._host is None:  # device-resident frame on a gloo group: stage through the host
             d, v = c.device()
             return d.cpu(), (v.cpu() if v is not None else None)
-        return (torch.from_numpy(np.ascontiguousarray(c._host)),
+        h = c._host if c.dictionary is None else np.asarray(c._host).astype(np.int32, copy=False)   # narrow host codes
+        return (torch.from_numpy(np.ascontiguousarray(h)),
                 torch.from_numpy(np.ascontiguousarray(c._host_valid)) if c._host_valid is not None else None)
 
     # grouped point-to-point transfers (NCCL fuses the batch into one all-to-all over NVLink; gloo,

@@ -837,11 +837,17 @@ def drift_numbers(args, src, rows, cols, rank, cat_every, torch, engine, synth):
 
 
 def host_copy(src, torch):
-    """Pinned host copy of every column (+ validity words, + the dictionary of string columns) of a device frame."""
+    """Pinned host copy of every column (+ validity words, + the dictionary of string columns) of a device frame.  Dictionary
+    codes are kept the way ColumnFrame.from_arrow keeps them on the host: in the narrowest integer type that holds the
+    dictionary (frame.narrow_code_dtype); the upload widens them on the device."""
+    import numpy as np
+    from anovos_b200.frame import narrow_code_dtype
     host = {}
     for name in src.columns:
         c = src.column(name)
         d, v = c.device()
+        if c.dictionary is not None:
+            d = d.to(getattr(torch, np.dtype(narrow_code_dtype(len(c.dictionary))).name))
         hd = torch.empty(d.shape, dtype=d.dtype, pin_memory=True)
         hd.copy_(d)
         hv = None
@@ -886,7 +892,7 @@ def e2e_numbers(args, rows, cols, host, torch, framemod, engine):
             "ms_each_step": [round(t * 1e3, 2) for t in times],
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (engine.d2h_bytes - d0) // steps,
             "h2d_gbs_lower_bound": h2d / dt / 1e9,   # the whole step's wall time charged to the copy: >= 50 means PCIe-bound
-            "steps": steps, "note": "pinned host columns -> pipelined H2D (profile.prefetch) -> 6 measures_of_* -> pandas, wall clock incl. host post-processing; MEDIAN of the steps (each listed: PCIe time varies with what else the host is doing)"}
+            "steps": steps, "note": "pinned host columns (string columns: dictionary codes in the narrowest of uint8 / int16 / int32, widened on the device) -> pipelined H2D (profile.prefetch) -> 6 measures_of_* -> pandas, wall clock incl. host post-processing; MEDIAN of the steps (each listed: PCIe time varies with what else the host is doing)"}
 
 
 # ---------------------------------------------------------------------------------------------

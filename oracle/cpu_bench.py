@@ -13,7 +13,9 @@ _TARGET = None
 
 
 def _stats_group(names):
+    import warnings
     from . import api as O
+    warnings.filterwarnings("ignore", message="No .* Computation", category=UserWarning)   # string-only column groups
     t = _TABLE.select(names)
     O.measures_of_counts(t)
     O.measures_of_centralTendency(t)

@@ -19,6 +19,8 @@ def _values(fr, name):
     col = fr.column(name)
     if col._host is not None:
         vals, words = np.asarray(col._host), col._host_valid
+        if col.dictionary is not None:
+            vals = vals.astype(np.int32, copy=False)      # host codes are stored narrow (frame.narrow_code_dtype)
     else:                                  # a column produced by a frame transform: CPU tensors under this stand-in
         vals = col._dev.numpy()
         words = None if col._dev_valid is None else col._dev_valid.numpy()
@@ -203,6 +205,8 @@ def _host_device(self):
         raise _lib.AnvError("column %r has dtype %s which the hot path does not process" % (self.name, self.sdtype))
     if self._dev is None:
         h = np.ascontiguousarray(self._host)
+        if self.dictionary is not None:
+            h = h.astype(np.int32, copy=False)
         self._dev = torch.from_numpy(h.copy() if not h.flags.writeable else h)
         if self._host_valid is not None:
             self._dev_valid = torch.from_numpy(np.ascontiguousarray(self._host_valid).copy())

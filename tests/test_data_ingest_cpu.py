@@ -146,3 +146,33 @@ def test_save_stats_layout(tmp_path):
     assert back.columns == ["attribute", "mean", "mode"] and back.count() == 2
     with pytest.raises(NotImplementedError):
         save_stats(None, df, str(tmp_path), "x", run_type="emr")
+
+
+def test_string_columns_keep_narrow_codes_on_the_host():
+    """from_arrow stores dictionary codes in uint8 / int16 / int32 by cardinality (fewer bytes over PCIe; the upload widens
+    them): the statistics, the arrow round trip and row slices are those of int32 codes."""
+    import numpy as np
+    import pyarrow as pa
+    import cpu_engine
+    from golden_util import assert_frames_match
+    from oracle import api as O
+    from anovos_b200.frame import ColumnFrame, narrow_code_dtype
+    import anovos.data_analyzer.stats_generator as sg
+    assert [np.dtype(narrow_code_dtype(k)).itemsize for k in (0, 1, 256, 257, 32768, 32769, 10 ** 6)] == [1, 1, 1, 2, 2, 4, 4]
+    n = 70_001
+    rng = np.random.default_rng(2)
+    cards = [3, 256, 300, 36_000]
+    t = pa.table({**{"s%d" % k: pa.array(["v%05d" % v for v in rng.permutation(np.arange(n) % k)], mask=rng.random(n) < 0.1) for k in cards},
+                  "x": pa.array(rng.normal(0, 1, n))})
+    fr = ColumnFrame.from_arrow(t)
+    assert [fr.column("s%d" % k)._host.dtype.itemsize for k in cards] == [1, 1, 2, 4]
+    assert fr.to_arrow().equals(t)
+    assert fr.slice_rows(64, 5000).to_arrow().equals(t.slice(64, 5000 - 64))
+    with cpu_engine.installed():
+        for f in ("measures_of_counts", "measures_of_centralTendency", "measures_of_cardinality"):
+            assert_frames_match(getattr(sg, f)(None, fr).toPandas(), getattr(O, f)(t))
+        wide = ColumnFrame.from_tensors({k: (fr.column(k)._host.astype(np.int32), fr.column(k)._host_valid, fr.column(k).dictionary)
+                                         for k in fr.columns if k != "x"}, n_rows=n)
+        narrow = ColumnFrame.from_tensors({k: (fr.column(k)._host, fr.column(k)._host_valid, fr.column(k).dictionary)
+                                           for k in fr.columns if k != "x"}, n_rows=n)
+        assert sg.measures_of_centralTendency(None, wide).toPandas().equals(sg.measures_of_centralTendency(None, narrow).toPandas())

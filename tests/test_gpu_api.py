@@ -659,3 +659,47 @@ def test_percentiles_of_partitions_beyond_the_head_buffer(sg):
     assert sg.measures_of_dispersion(None, tt).toPandas()["IQR"].tolist() == O.measures_of_dispersion(tt)["IQR"].tolist()
     assert sg.measures_of_centralTendency(None, tt).toPandas()["median"].tolist() == O.measures_of_centralTendency(tt)["median"].tolist()
     assert not O.measures_of_percentiles(t).equals(exp)
+
+
+def test_narrow_host_codes_upload_like_int32(sg):
+    """String columns keep their dictionary codes on the host in uint8 / int16 / int32 by cardinality; lazy upload and the
+    prefetch pipeline widen them on the device, and every statistic equals the one of the same frame with int32 host codes
+    and the oracle's."""
+    import torch
+    from anovos_b200 import profile
+    from anovos_b200.frame import ColumnFrame, narrow_code_dtype
+    n = 200_003
+    rng = np.random.default_rng(9)
+    cards = [2, 200, 256, 257, 30_000, 40_000]
+    cols = {"s%d" % k: pa.array(["v%05d" % v for v in rng.integers(0, k, n)], mask=rng.random(n) < 0.05) for k in cards}
+    cols["x"] = pa.array(rng.normal(0, 1, n).astype(np.float32))
+    t = pa.table(cols)
+    fr = ColumnFrame.from_arrow(t)
+    for k in cards:
+        c = fr.column("s%d" % k)
+        assert c._host.dtype == narrow_code_dtype(len(c.dictionary))
+    assert [fr.column("s%d" % k)._host.dtype.itemsize for k in cards] == [1, 1, 1, 2, 2, 4]
+    wide = {}
+    for name in fr.columns:
+        c = fr.column(name)
+        h = torch.from_numpy(c._host.astype(np.int32) if c.dictionary is not None else c._host)
+        hv = None if c._host_valid is None else torch.from_numpy(c._host_valid)
+        wide[name] = (h, hv, c.dictionary) if c.dictionary is not None else ((h, hv) if hv is not None else h)
+    narrow = {name: ((torch.from_numpy(fr.column(name)._host).pin_memory(),) + tuple(v[1:]) if isinstance(v, tuple) and len(v) == 3 else v)
+              for name, v in wide.items()}
+    a = ColumnFrame.from_tensors(wide, n_rows=n)
+    b = ColumnFrame.from_tensors(narrow, n_rows=n)
+    profile.prefetch(b, group=3)
+    for name in fr.columns:
+        d, _ = fr.column(name).device()
+        d2, _ = b.column(name).device()
+        if fr.column(name).dictionary is not None:
+            assert d.dtype == torch.int32 and d2.dtype == torch.int32
+            assert torch.equal(d, a.column(name).device()[0]) and torch.equal(d2, d)
+    for f in ("measures_of_counts", "measures_of_centralTendency", "measures_of_cardinality"):
+        x, y, z = (getattr(sg, f)(None, q).toPandas() for q in (a, b, fr))
+        assert x.equals(y) and x.equals(z), f
+        exp = getattr(O, f)(t)
+        from golden_util import assert_frames_match
+        assert_frames_match(x, exp)
+    assert fr.to_arrow().equals(t)
