@@ -146,7 +146,7 @@ def _discrete_cols(fr, list_of_cols, drop_cols, allow_empty=False):
         num, cat, _ = attributeType_segregation(fr)
         list_of_cols = num + cat
     cols = _unique(_names(list_of_cols), _names(drop_cols))
-    if any(c not in fr.columns for c in cols) or (not cols and not allow_empty):
+    if any(c not in fr for c in cols) or (not cols and not allow_empty):
         raise TypeError("Invalid input for Column(s)")
     bad = [c for c in cols if fr.column(c).kind == "other"]
     if bad:
@@ -160,7 +160,8 @@ def _numeric_cols(fr, list_of_cols, drop_cols):
     if isinstance(list_of_cols, str) and list_of_cols == "all":
         list_of_cols = num
     cols = _unique(_names(list_of_cols), _names(drop_cols))
-    if any(c not in num for c in cols):
+    numset = set(num)
+    if any(c not in numset for c in cols):
         raise TypeError("Invalid input for Column(s)")
     return cols
 
@@ -207,9 +208,9 @@ def measures_of_counts(spark, idf, list_of_cols="all", drop_cols=[], print_impac
     else:
         fill_pct = miss_pct = nz_pct = np.full(len(cols), np.nan)
     nz_col = nz if is_num.all() else np.where(is_num, nz.astype(np.float64), np.nan)   # string columns: null
-    odf = pd.DataFrame({"attribute": cols, "fill_count": fill, "fill_pct": _opt(fill_pct), "missing_count": N - fill,
-                        "missing_pct": _opt(miss_pct), "nonzero_count": nz_col, "nonzero_pct": _opt(nz_pct)}, copy=False)
-    return _show(ResultFrame(odf), len(cols), print_impact)
+    odf = ResultFrame.from_columns({"attribute": cols, "fill_count": fill, "fill_pct": _opt(fill_pct), "missing_count": N - fill,
+                                    "missing_pct": _opt(miss_pct), "nonzero_count": nz_col, "nonzero_pct": _opt(nz_pct)})
+    return _show(odf, len(cols), print_impact)
 
 
 def _mode_str(col, value):
@@ -238,23 +239,34 @@ def measures_of_centralTendency(spark, idf, list_of_cols="all", drop_cols=[], pr
     """reference :424-526: mean, median (numeric only), mode, mode_rows, mode_pct."""
     fr = as_frame(idf)
     cols = _discrete_cols(fr, list_of_cols, drop_cols)
-    num = [c for c in cols if fr.column(c).kind == "num"]
+    kinds = [fr.column(c) for c in cols]
+    num = [c for c, col in zip(cols, kinds) if col.kind == "num"]
     m = profile.moments(fr, num)
     nvd = profile.n_valid(fr, cols)             # string columns: from their code histogram (no second pass over them)
     md = profile.mode_distinct(fr, cols)       # the sort also yields the exact percentiles (cached)
     med = profile.quantiles(fr, num, [0.5])
-    rows = []
-    for c in cols:
-        col = fr.column(c)
-        nv = nvd[c]
-        mean = median = None
-        if col.kind == "num" and nv:
-            mean = _R(float(m[c]["mean"]))
-            median = _R(_disp(col, med[c][0]))
-        mode, rows_ = md[c][0], md[c][1]
-        rows.append([c, mean, median, _mode_str(col, mode), rows_, None if rows_ is None else _R(rows_ / nv)])
-    odf = pd.DataFrame(rows, columns=["attribute", "mean", "median", "mode", "mode_rows", "mode_pct"])
-    return _show(ResultFrame(odf), len(cols), print_impact)
+    k = len(cols)
+    nv = np.array([nvd[c] for c in cols], dtype=np.float64)
+    mean, median = np.full(k, np.nan), np.full(k, np.nan)
+    mode, mode_rows = [None] * k, np.full(k, np.nan)
+    for i, (c, col) in enumerate(zip(cols, kinds)):
+        if col.kind == "num" and nv[i]:
+            mean[i] = m[c]["mean"]
+            v = med[c][0]
+            median[i] = np.nan if v is None else v
+        mo, rows_ = md[c][0], md[c][1]
+        mode[i] = _mode_str(col, mo)
+        if rows_ is not None:
+            mode_rows[i] = rows_
+    fl = np.array([col.sdtype == "float" for col in kinds], dtype=bool) & np.isfinite(median)
+    if fl.any():
+        median[fl] = _f32_trip(median[fl])                      # FloatType: Float.toString round trip (_disp)
+    with np.errstate(all="ignore"):
+        pct = spark_round_array(np.where(nv > 0, mode_rows / nv, np.nan))
+    has_null_rows = np.isnan(mode_rows).any()
+    odf = ResultFrame.from_columns({"attribute": cols, "mean": spark_round_array(mean), "median": spark_round_array(median), "mode": mode,
+                                    "mode_rows": mode_rows if has_null_rows else mode_rows.astype(np.int64), "mode_pct": pct})
+    return _show(odf, len(cols), print_impact)
 
 
 def _unique_values(fr, cols, approx, rsd):
@@ -302,10 +314,13 @@ def measures_of_cardinality(spark, idf, list_of_cols="all", drop_cols=[], use_ap
         return _empty(["attribute", "unique_values", "IDness"])
     u = _unique_values(fr, cols, use_approx_unique_count, rsd)
     nv = profile.n_valid(fr, cols)
-    rows = [[c, int(u[c][0]), _R(u[c][0] / nv[c]) if nv[c] else None] for c in cols]
-    odf = pd.DataFrame(rows, columns=["attribute", "unique_values", "IDness"])
-    odf.attrs["hll_bias_band"] = [c for c in cols if u[c][1]]
-    return _show(ResultFrame(odf), len(cols), print_impact)
+    uv = np.array([int(u[c][0]) for c in cols], dtype=np.int64)
+    nva = np.array([nv[c] for c in cols], dtype=np.float64)
+    with np.errstate(all="ignore"):
+        idness = spark_round_array(np.where(nva > 0, uv / nva, np.nan))
+    odf = ResultFrame.from_columns({"attribute": cols, "unique_values": uv, "IDness": idness},
+                                   attrs={"hll_bias_band": [c for c in cols if u[c][1]]})
+    return _show(odf, len(cols), print_impact)
 
 
 def _stddev(rec):
@@ -322,24 +337,25 @@ def measures_of_dispersion(spark, idf, list_of_cols="all", drop_cols=[], print_i
     if not cols:
         warnings.warn("No Dispersion Computation - No numerical column(s) to analyze")
         return _empty(["attribute", "stddev", "variance", "cov", "IQR", "range"])
-    m = profile.moments(fr, cols)
+    m = profile.moments_table(fr, cols)
     q = profile.quantiles(fr, cols, [0.25, 0.75])
     k = len(cols)
-    nv = np.array([int(m[c]["n_valid"]) for c in cols])
-    m2 = np.array([float(m[c]["m2"]) for c in cols])
-    mean = np.array([float(m[c]["mean"]) for c in cols])
+    nv, m2, mean = m["n_valid"], m["m2"], m["mean"]
     raw = np.full((k, 4), np.nan)                     # q25, q75, min, max (display values)
+    raw[:, 2], raw[:, 3] = m["min"], m["max"]
     for i, c in enumerate(cols):
         if nv[i]:
-            raw[i] = (q[c][0], q[c][1], float(m[c]["min"]), float(m[c]["max"]))
+            raw[i, 0], raw[i, 1] = q[c]
+        else:
+            raw[i] = np.nan
     with np.errstate(all="ignore"):
         sd = spark_round_array(np.where(nv > 1, np.sqrt(m2 / np.maximum(nv - 1, 1)), np.nan))   # n <= 1: null (Spark >= 3.1)
         var = spark_round_array(sd * sd)
         cov = spark_round_array(np.where(mean == 0, np.nan, sd / mean))                           # x / 0 is null in Spark SQL
         iqr = spark_round_array(_disp_diff(fr, cols, raw[:, 1].copy(), raw[:, 0].copy()))
         rng = spark_round_array(_disp_diff(fr, cols, raw[:, 3].copy(), raw[:, 2].copy()))
-    odf = pd.DataFrame({"attribute": cols, "stddev": sd, "variance": var, "cov": cov, "IQR": iqr, "range": rng})
-    return _show(ResultFrame(odf), len(cols), print_impact)
+    odf = ResultFrame.from_columns({"attribute": cols, "stddev": sd, "variance": var, "cov": cov, "IQR": iqr, "range": rng})
+    return _show(odf, len(cols), print_impact)
 
 
 _PCT = [("1%", 0.01), ("5%", 0.05), ("10%", 0.1), ("25%", 0.25), ("50%", 0.5), ("75%", 0.75), ("90%", 0.9),
@@ -355,18 +371,21 @@ def measures_of_percentiles(spark, idf, list_of_cols="all", drop_cols=[], print_
     if not cols:
         warnings.warn("No Percentiles Computation - No numerical column(s) to analyze")
         return _empty(names)
-    m = profile.moments(fr, cols)
+    m = profile.moments_table(fr, cols)
     q = profile.quantiles(fr, cols, [p for _, p in _PCT])
     vals = np.full((len(cols), 11), np.nan)
+    vals[:, 0], vals[:, 10] = m["min"], m["max"]
+    nonempty = m["n_valid"] > 0
     for i, c in enumerate(cols):
-        rec = m[c]
-        if int(rec["n_valid"]):
-            vals[i, 0], vals[i, 10] = rec["min"], rec["max"]
+        if nonempty[i]:
             vals[i, 1:10] = [np.nan if v is None else v for v in q[c]]
+        else:
+            vals[i] = np.nan
     vals = spark_round_array(_disp_matrix(fr, cols, vals))
-    odf = pd.DataFrame(vals, columns=names[1:])
-    odf.insert(0, "attribute", cols)
-    return _show(ResultFrame(odf), len(cols), print_impact)
+    data = {"attribute": cols}
+    for j, nme in enumerate(names[1:]):
+        data[nme] = vals[:, j]
+    return _show(ResultFrame.from_columns(data), len(cols), print_impact)
 
 
 def measures_of_shape(spark, idf, list_of_cols="all", drop_cols=[], print_impact=False):
@@ -376,14 +395,10 @@ def measures_of_shape(spark, idf, list_of_cols="all", drop_cols=[], print_impact
     if not cols:
         warnings.warn("No Skewness/Kurtosis Computation - No numerical column(s) to analyze")
         return _empty(["attribute", "skewness", "kurtosis"])
-    m = profile.moments(fr, cols)
-    n = np.array([int(m[c]["n_valid"]) for c in cols], dtype=np.float64)
-    m2 = np.array([float(m[c]["m2"]) for c in cols])
-    m3 = np.array([float(m[c]["m3"]) for c in cols])
-    m4 = np.array([float(m[c]["m4"]) for c in cols])
+    m = profile.moments_table(fr, cols)
+    n, m2, m3, m4 = m["n_valid"].astype(np.float64), m["m2"], m["m3"], m["m4"]
     with np.errstate(all="ignore"):
         ok = (n > 0) & (m2 != 0)                 # Spark >= 3.1: null when M2 == 0 (parity unpinned)
         skew = spark_round_array(np.where(ok, np.sqrt(n) * m3 / np.sqrt(m2 * m2 * m2), np.nan))
         kurt = spark_round_array(np.where(ok, n * m4 / (m2 * m2) - 3.0, np.nan))
-    odf = pd.DataFrame({"attribute": cols, "skewness": _opt(skew), "kurtosis": _opt(kurt)}, copy=False)
-    return _show(ResultFrame(odf), len(cols), print_impact)
+    return _show(ResultFrame.from_columns({"attribute": cols, "skewness": _opt(skew), "kurtosis": _opt(kurt)}), len(cols), print_impact)

@@ -14,10 +14,17 @@ _QUANT = {4: Decimal("0.0001")}
 def attributeType_segregation(idf):
     """-> (num_cols, cat_cols, other_cols) by Spark dtype string (shared/utils.py:64-72)."""
     fr = as_frame(idf)
-    out = {"num": [], "cat": [], "other": []}
-    for name, sd in fr.dtypes:
-        out[kind_of(sd)].append(name)
-    return out["num"], out["cat"], out["other"]
+    seg = getattr(fr, "_segregation", None)        # frames are immutable: the split is computed once per frame
+    if seg is None:
+        out = {"num": [], "cat": [], "other": []}
+        for name, sd in fr.dtypes:
+            out[kind_of(sd)].append(name)
+        seg = (tuple(out["num"]), tuple(out["cat"]), tuple(out["other"]))
+        try:
+            fr._segregation = seg
+        except AttributeError:
+            pass
+    return list(seg[0]), list(seg[1]), list(seg[2])
 
 
 def get_dtype(idf, col):
@@ -111,6 +118,8 @@ def jvm_double_str(x: float) -> str:
         return "Infinity" if x > 0 else "-Infinity"
     if x == 0:
         return "-0.0" if math.copysign(1.0, x) < 0 else "0.0"
+    if 1e-3 <= abs(x) < 1e7:
+        return repr(x)      # Python prints the same shortest digits in plain decimal notation over this range
     sign, digits, exp = Decimal(repr(x)).as_tuple()
     ds = "".join(map(str, digits)).rstrip("0") or "0"
     exp += len(digits) - len(ds) if ds != "0" else 0
