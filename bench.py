@@ -281,7 +281,13 @@ def _run_ours(args, out):
             alg += n_keys * 4 * PARTITION_WORDS_PER_KEY
         ach = alg / (ms_step * 1e-3) / 1e9 if (alg and ms_step > 0) else None
         traffic = traffic_tbl.get(call)
-        return {"kernel": KERNEL_NAMES.get(call, {"anv_mode_distinct": SORT_DESIGN, "anv_mode_distinct_partition": PARTITION_DESIGN}.get(call, call)),
+        more = {}
+        if call == "anv_mode_distinct" and ms_step > 0:
+            # context for an issue-bound kernel: keys sorted per second (pack, run summaries and HLL++ registers included in the
+            # time) next to the CUDA toolkit's radix sort on the same GPU (recorded by scripts/yardstick/cub_sort.cu)
+            more = {"sorted_keys_per_step": n_keys, "gkeys_per_s_incl_pack_and_summaries": n_keys / (ms_step * 1e-3) / 1e9,
+                    "library_yardstick": library_yardstick(rows)}
+        return {**more, "kernel": KERNEL_NAMES.get(call, {"anv_mode_distinct": SORT_DESIGN, "anv_mode_distinct_partition": PARTITION_DESIGN}.get(call, call)),
                 "call": call,
                 "bound": BOUND.get(call, "hbm"), "achieved": ach, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak if ach else None,
@@ -305,7 +311,19 @@ def _run_ours(args, out):
             rowslab = rowslab_check(rank, world, torch, dist)
         except Exception as ex:
             rowslab = {"error": repr(ex)}
+    # N > 1: the end-to-end leg runs on EVERY rank at once (each GPU pulls its own columns over its own PCIe link) when the
+    # host has room for all the pinned copies; otherwise rank 0 measures its share alone and says so
+    e2e_all = False
+    if world > 1 and not args.no_extras:
+        e2e_all = all_ranks_have_host_room(rows, cols, world, torch, dist)
     line = None
+    if rank != 0 and e2e_all:
+        holder = [src]
+        src = None
+        try:
+            e2e_numbers(args, rows, cols, holder, torch, framemod, engine, dist=dist, world=world)
+        except Exception as ex:      # reported by rank 0 as a rank-0-only measurement; never take the job down
+            print("rank %d: end-to-end leg failed: %r" % (rank, ex), file=sys.stderr)
     if rank == 0:
         extra, e2e, cpu, parity = {}, None, None, None
         if not args.no_extras:
@@ -328,12 +346,13 @@ def _run_ours(args, out):
             else:
                 parity = {"skipped": "N > 1 runs the identical per-rank path on other column ids: see the N = 1 line (or pass --parity)"}
             # ---- e2e: same step from pinned HOST buffers through the public API ---------------------
-            host = host_copy(src, torch)
-            src = None   # free the resident frame: at c3 (80 GB) it would not fit twice
-            torch.cuda.empty_cache()
-            e2e = e2e_numbers(args, rows, cols, host, torch, framemod, engine)
-            e2e["numa"] = numa
-            del host
+            holder = [src]
+            src = None   # the leg frees the resident frame once it is copied: at c3 (80 GB) it would not fit twice
+            try:
+                e2e = e2e_numbers(args, rows, cols, holder, torch, framemod, engine, dist=dist if e2e_all else None, world=world)
+                e2e["numa"] = numa
+            except Exception as ex:
+                e2e = {"error": repr(ex)}
             cpu = cpu_baseline(cols, cat_every=cat_every, first_col=rank * cols)
         line = {"metric": METRIC, "value": value, "unit": "rows*cols/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -354,6 +373,20 @@ def _run_ours(args, out):
         dist.destroy_process_group()
     if line is not None:
         out.emit(json.dumps(line))
+
+
+def library_yardstick(rows):
+    """cub::DeviceRadixSort::SortKeys (bare sort of uniform 32-bit keys) as recorded under profiles/ for this row count."""
+    for cand in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        if "cub_yardstick" in cand and cand.endswith(".json"):
+            try:
+                for e in json.load(open(os.path.join(ROOT, "profiles", cand)))["library"]:
+                    if e["key_bits"] == 32 and e["n_keys"] == rows:
+                        return {"library": e["library"], "gkeys_per_s": e["gkeys_per_s"], "ms_per_column": e["ms_per_column"],
+                                "what": "bare key sort, no pack / run summaries / HLL++", "source": "profiles/" + cand}
+            except Exception:
+                pass
+    return None
 
 
 def rowslab_check(rank, world, torch, dist):
@@ -862,12 +895,33 @@ def host_copy(src, torch):
     return host
 
 
-def e2e_numbers(args, rows, cols, host, torch, framemod, engine):
+def all_ranks_have_host_room(rows, cols, world, torch, dist):
+    """Collective: may every rank of this node pin its own host copy of the frame at the same time?"""
+    try:
+        import psutil
+        need = rows * cols * 4 * 1.05
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        ok = psutil.virtual_memory().available > need * local_world * 1.3 + 32e9
+    except Exception:
+        ok = False
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
+def dist_rank(torch):
+    import torch.distributed as td
+    return td.get_rank() if td.is_available() and td.is_initialized() else 0
+
+
+def e2e_numbers(args, rows, cols, src_holder, torch, framemod, engine, dist=None, world=1):
     """Full step from pinned host buffers: H2D of every column + the result read-back inside
-    the timed region, through ColumnFrame.from_tensors + the stats_generator API."""
+    the timed region, through ColumnFrame.from_tensors + the stats_generator API.  With `dist` every rank runs it at the same
+    time on its own columns (barrier before each step, MAX over ranks of each step's wall time): the whole-job number."""
     steps = max(1, min(args.steps, 5 if rows * cols <= 2_000_000_000 else 3))
 
     from anovos_b200 import profile
+    host = None
 
     def one():
         fr = framemod.ColumnFrame.from_tensors(host, n_rows=rows)
@@ -876,23 +930,52 @@ def e2e_numbers(args, rows, cols, host, torch, framemod, engine):
         del fr
         return r
 
-    for _ in range(5):   # the copy-stream memory pool needs a few rounds to reach its steady size
-        one()
-    torch.cuda.synchronize()
+    failure = None
+    try:
+        host = host_copy(src_holder.pop(), torch)     # `src_holder` = [device frame]: released here, it would not fit twice
+        torch.cuda.empty_cache()
+        for _ in range(5):   # the copy-stream memory pool needs a few rounds to reach its steady size
+            one()
+        torch.cuda.synchronize()
+    except Exception as ex:
+        failure = ex
+    if dist is not None:     # go on together only if EVERY rank got this far (a rank that could not pin its copy must not leave the others in a barrier)
+        flag = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            dist = None
+            if dist_rank(torch) != 0 and failure is None:
+                return None
+    if failure is not None:
+        raise failure
     h0, d0 = framemod.h2d_bytes, engine.d2h_bytes
     times = []
     for _ in range(steps):
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
         one()
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
+    h2d, d2h = (framemod.h2d_bytes - h0) // steps, (engine.d2h_bytes - d0) // steps
+    ranks = 1
+    if dist is not None:
+        tt = torch.tensor(times + [float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        times = mx[:steps].tolist()
+        h2d, d2h = int(tt[steps].item()), int(tt[steps + 1].item())     # whole job: summed over the ranks
+        ranks = world
     dt = sorted(times)[len(times) // 2]     # median: one step that collides with another tenant's PCIe / host traffic is listed, not averaged in
-    h2d = (framemod.h2d_bytes - h0) // steps
-    return {"value": rows * cols / dt, "unit": "rows*cols/s", "ms_per_step": dt * 1e3,
+    return {"value": ranks * rows * cols / dt, "unit": "rows*cols/s", "ms_per_step": dt * 1e3,
             "ms_each_step": [round(t * 1e3, 2) for t in times],
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (engine.d2h_bytes - d0) // steps,
-            "h2d_gbs_lower_bound": h2d / dt / 1e9,   # the whole step's wall time charged to the copy: >= 50 means PCIe-bound
-            "steps": steps, "note": "pinned host columns (string columns: dictionary codes in the narrowest of uint8 / int16 / int32, widened on the device) -> pipelined H2D (profile.prefetch) -> 6 measures_of_* -> pandas, wall clock incl. host post-processing; MEDIAN of the steps (each listed: PCIe time varies with what else the host is doing)"}
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "h2d_gbs_lower_bound": h2d / dt / 1e9,   # the whole step's wall time charged to the copy: >= 50 per GPU means PCIe-bound
+            "steps": steps, "ranks_measured": ranks,
+            "scope": ("all %d ranks at once, each from its own pinned host copy over its own PCIe link; step time = MAX over ranks" % ranks) if ranks > 1
+                     else ("this rank's columns only" + (" (N > 1: the host cannot pin every rank's copy at once - the other ranks idle)" if world > 1 else "")),
+            "note": "pinned host columns (string columns: dictionary codes in the narrowest of uint8 / int16 / int32, widened on the device) -> pipelined H2D (profile.prefetch) -> 6 measures_of_* -> pandas, wall clock incl. host post-processing; MEDIAN of the steps (each listed: PCIe time varies with what else the host is doing)"}
 
 
 # ---------------------------------------------------------------------------------------------
