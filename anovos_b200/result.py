@@ -24,6 +24,8 @@ def build_frame(columns: dict, attrs=None) -> pd.DataFrame:
     names = list(columns)
     n = len(columns[names[0]]) if names else 0
     try:
+        if n == 0:
+            raise TypeError("empty result: let the pandas constructor infer the dtypes")
         df = pd.DataFrame._from_arrays([_column_array(columns[k]) for k in names], columns=pd.Index(names), index=pd.RangeIndex(n),
                                        verify_integrity=False)
     except (AttributeError, TypeError):          # a pandas without the fast constructor

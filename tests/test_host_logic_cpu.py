@@ -114,3 +114,29 @@ def test_frames_to_matrix_aligns_frames_of_different_row_counts():
     assert m[:, 0].tolist() == [3.0, 2.0, 3.0]
     assert m[0, 1] == 0.5 and np.isnan(m[1, 1]) and np.isnan(m[2, 1])
     assert m[0, 2] == 1.0 and np.isnan(m[1, 2]) and m[2, 2] == 2.0
+
+
+def test_result_frames_equal_the_plain_pandas_constructor():
+    """ResultFrame.from_columns builds its frame through pandas' array constructor: values AND dtypes must be the ones
+    pd.DataFrame(dict) infers; every toPandas() hands out an independent frame."""
+    import numpy as np
+    import pandas as pd
+    from anovos_b200.result import ResultFrame, build_frame
+    cases = [
+        {"attribute": ["a", "b", "c"], "n": np.array([1, 2, 3], dtype=np.int64), "x": np.array([0.5, np.nan, 2.0]),
+         "mode": ["1.0", None, "x"], "none": [None, None, None], "mixed": [1.5, None, 2.0]},
+        {"attribute": [], "x": np.zeros(0)},
+        {"attribute": ["only"], "flag": np.array([True]), "s": ["v"]},
+    ]
+    for cols in cases:
+        exp = pd.DataFrame({k: (v.copy() if isinstance(v, np.ndarray) else list(v)) for k, v in cols.items()})
+        got = build_frame(cols)
+        assert list(got.columns) == list(exp.columns) and got.dtypes.tolist() == exp.dtypes.tolist(), (got.dtypes, exp.dtypes)
+        assert got.equals(exp)
+        rf = ResultFrame.from_columns(cols, attrs={"k": [1]})
+        a, b = rf.toPandas(), rf.toPandas()
+        assert a.equals(exp) and a.attrs == {"k": [1]} and rf.columns == list(cols) and rf.count() == len(exp)
+        if len(a):
+            a.iloc[0, 0] = "changed"
+            assert b.equals(exp) and rf.toPandas().equals(exp)
+            assert rf.where({"attribute": cols["attribute"][0]}).count() == 1
