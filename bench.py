@@ -901,7 +901,20 @@ def all_ranks_have_host_room(rows, cols, world, torch, dist):
         import psutil
         need = rows * cols * 4 * 1.05
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-        ok = psutil.virtual_memory().available > need * local_world * 1.3 + 32e9
+        avail = psutil.virtual_memory().available
+        for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):   # a container limit counts too
+            try:
+                lim = open(path).read().strip()
+                if lim.isdigit():
+                    used = 0
+                    for up in ("/sys/fs/cgroup/memory.current", "/sys/fs/cgroup/memory/memory.usage_in_bytes"):
+                        if os.path.exists(up):
+                            used = int(open(up).read().strip())
+                            break
+                    avail = min(avail, int(lim) - used)
+            except OSError:
+                pass
+        ok = avail > need * local_world * 1.5 + 64e9
     except Exception:
         ok = False
     t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
