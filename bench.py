@@ -72,24 +72,55 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polling the SM clock and the throttle reasons every 200 ms (the profiling recipe's line).  The process is started BEFORE the warm-up: its
+    start-up (NVML init over every GPU of the box) takes about a second of driver work and used to land inside the timed
+    region of short runs; begin() waits for its first sample and opens the window, stop() keeps the samples taken inside it."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.path = gpu_index, None, "/tmp/anv_clocks_%d.csv" % os.getpid()
+        self.t_begin = None
+        self.period_ms = int(os.environ.get("ANV_BENCH_CLOCK_PERIOD_MS", "200"))   # the profiling recipe's period; 0 = diagnostics only: no sampling
+        self.disabled = self.period_ms <= 0
 
     def start(self):
+        if self.disabled:
+            return
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", str(self.period_ms), "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def begin(self):
+        """Open the sampling window (call right before the timed region; starts the sampler if start() was not called)."""
+        if self.proc is None and not self.disabled:
+            self.start()
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < 5.0:      # the sampler is past its start-up once a line is out
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                break
+            time.sleep(0.02)
+        self.t_begin = time.time()
+
+    @staticmethod
+    def _when(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled (ANV_BENCH_CLOCK_PERIOD_MS=0)" if self.disabled else "nvidia-smi unavailable"]}
+        t_end = time.time()
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -97,28 +128,29 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in open(self.path):
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                rows.append((self._when(parts[0]), float(parts[1]), float(parts[2]),
+                             [nme for nme, v in zip(names, parts[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nme, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
         try:
             os.remove(self.path)
         except OSError:
             pass
-        if not sm:
+        if self.t_begin is not None:
+            inside = [r for r in rows if r[0] is not None and self.t_begin - 0.1 <= r[0] <= t_end + 0.15]
+            rows = inside or rows       # a timed region shorter than the polling period: keep what there is
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted({x for r in rows for x in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in rows), "reasons": reasons, "samples": len(rows)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -223,15 +255,17 @@ def _run_ours(args, out):
 
     if not args.no_extras:
         args.warmup = max(args.warmup, 3)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         step()
     drain()
     barrier()
     engine.timer = engine.KernelTimer()
     l0 = engine.launch_count
-    clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -563,13 +597,14 @@ def _run_c1(args, out, wl, world, rank, local):
         fr._cache = {k: v for k, v in fr._cache.items() if isinstance(k, tuple) and k and k[0] == "desc"}
         return sg.measures_of_centralTendency(None, fr).toPandas()
 
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     engine.timer = engine.KernelTimer()
     l0 = engine.launch_count
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -680,14 +715,16 @@ def _run_stream(args, out, wl, rows, cols, world, rank, local):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(max(args.warmup, 1) if rows > 50_000_000 else max(args.warmup, 3)):
         step()
     barrier()
     engine.timer = engine.KernelTimer()
     l0 = engine.launch_count
-    clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
