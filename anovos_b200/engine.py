@@ -510,12 +510,14 @@ def hll_estimate_from_registers(regs: np.ndarray, p: int):
     return int(math.floor(e + 0.5)), True
 
 
+_POW2_NEG = np.ldexp(1.0, -np.arange(128))
+
+
 def hll_estimates_from_register_rows(R: np.ndarray, p: int):
     """hll_estimate_from_registers for every row of R [n_cols, 2**p] at once -> list of (estimate, in_bias_band)."""
     m = 1 << p
-    Ri = R.astype(np.int64)
-    z = np.ldexp(1.0, -Ri).sum(axis=1)
-    v = (Ri == 0).sum(axis=1)
+    z = _POW2_NEG[R].sum(axis=1)             # 2^-register, exact (registers are <= 64 - p + 1)
+    v = m - np.count_nonzero(R, axis=1)
     alpha = {4: 0.673, 5: 0.697, 6: 0.709}.get(p, 0.7213 / (1.0 + 1.079 / m))
     e = alpha * m * m / z
     out = []
@@ -597,11 +599,12 @@ def hll_estimates(frame: ColumnFrame, names, p: int):
         # per-row work (the code histogram) runs on the device; every dictionary entry is hashed on the host ONCE per
         # dictionary (cached: register index and rho of each entry), so a step only takes a masked maximum
         cc = code_counts(frame, cat)
-        for n, h in zip(cat, cc):
+        R = np.zeros((len(cat), m), np.uint32)
+        for i, (n, h) in enumerate(zip(cat, cc)):
             idx, rho = _dictionary_hll(frame.column(n).dictionary, p)
-            regs = np.zeros(m, np.uint32)
             present = np.flatnonzero(h[1:])
             if present.size:
-                np.maximum.at(regs, idx[present], rho[present])
-            out[n] = hll_estimate_from_registers(regs, p)
+                np.maximum.at(R[i], idx[present], rho[present])
+        for n, r in zip(cat, hll_estimates_from_register_rows(R, p)):
+            out[n] = r
     return [out[n] for n in names]

@@ -65,24 +65,36 @@ def quantiles(frame: ColumnFrame, names, probs, eps=SUMMARY_EPS):
                         gc[(n, p)] = v
         if all((n, p) in gc for n in names for p in probs):
             return {n: [gc[(n, p)] for p in probs] for n in names}
-    c = _cache(frame, "quantiles")
-    mom = moments(frame, names)
+    c = _cache(frame, "quantiles")          # name -> {1-based rank: order statistic}
     rc = _cache(frame, "quantile_ranks")
     pk = (tuple(probs), eps)
     want = {}
+    mom = None
     for n in names:
         r = rc.get((n, pk))
         if r is None:
+            if mom is None:
+                mom = moments(frame, names)
             r = rc[(n, pk)] = engine.quantile_ranks(int(mom[n]["n_valid"]), probs, eps)
         want[n] = r
-    todo = [n for n in names if any(r and (n, r) not in c for r in want[n])]
+    todo = []
+    for n in names:
+        have = c.get(n)
+        if have is None:
+            have = c[n] = {}
+        for r in want[n]:
+            if r and r not in have:
+                todo.append(n)
+                break
     if todo:
         # a select pass costs the same for 1 or 16 ranks: always resolve the nine summary() percentiles too, so
         # median / IQR / percentiles share ONE radix select per column
+        if mom is None:
+            mom = moments(frame, names)
         sets = {}
         for n in todo:
             extra = engine.quantile_ranks(int(mom[n]["n_valid"]), SUMMARY_PROBS, SUMMARY_EPS)
-            sets[n] = sorted(set(r for r in want[n] + extra if r and (n, r) not in c))
+            sets[n] = sorted(set(r for r in want[n] + extra if r and r not in c[n]))
         width = max(len(v) for v in sets.values())
         rk = np.zeros((len(todo), max(width, 1)), np.int64)
         for i, n in enumerate(todo):
@@ -90,10 +102,13 @@ def quantiles(frame: ColumnFrame, names, probs, eps=SUMMARY_EPS):
             rk[i, :len(rs)] = rs
         vals = engine.select_ranks(frame, todo, rk)
         for i, n in enumerate(todo):
-            for r, v in zip(rk[i], vals[i]):
-                if r:
-                    c[(n, int(r))] = float(v)
-    return {n: [c[(n, r)] if r else None for r in want[n]] for n in names}
+            k = len(sets[n])
+            c[n].update(zip(sets[n], vals[i, :k].tolist()))
+    out = {}
+    for n in names:
+        have = c[n]
+        out[n] = [have[r] if r else None for r in want[n]]
+    return out
 
 
 def code_counts(frame: ColumnFrame, names):
@@ -142,11 +157,14 @@ def mode_distinct(frame: ColumnFrame, names):
                     hc.setdefault(n, r)
         else:
             res, vals = engine.sort_mode_distinct(frame, num, rk)
+        rkl, vl = rk.tolist(), vals.tolist()
         for i, n in enumerate(num):
             c[n] = res[i]
-            for r, v in zip(rk[i], vals[i]):
-                if r:
-                    qc[(n, int(r))] = float(v)
+            d = qc.get(n)
+            if d is None:
+                d = qc[n] = {}
+            d.update(zip(rkl[i], vl[i]))
+            d.pop(0, None)                     # rank 0 = "skip" (empty column)
     return {n: c[n] for n in names}
 
 

@@ -37,7 +37,7 @@ def _fill_cache(fr: ColumnFrame, table: pa.Table):
             else:
                 rec["min"] = rec["max"] = rec["mean"] = np.nan
             for r in range(1, p.n + 1) if p.n <= 64 else set(engine.quantile_ranks(p.n, profile.SUMMARY_PROBS, profile.SUMMARY_EPS)):
-                q[(name, int(r))] = float(p.sorted64[r - 1])
+                q.setdefault(name, {})[int(r)] = float(p.sorted64[r - 1])
             mv, mr = p.mode()
             mode[name] = (float(mv), int(mr), p.distinct()) if p.n else (None, None, 0)
         else:
