@@ -46,6 +46,8 @@ struct ScanParams {
   // bin-id materialisation
   int32_t* out_bins;
   int64_t out_stride;
+  // cp.async staging ring of the STAGED kernels: byte offset inside the dynamic shared memory (behind the counters)
+  uint32_t stage_off;
 };
 
 // Per-kernel tuning (measured on B200, scripts/tune.sh): 8 x 128-bit loads in flight per
@@ -66,6 +68,33 @@ template <bool MOM, int HPATH, bool ASSIGN> struct Tune {
   static constexpr bool PF = !MOM && HPATH == 0 && !ASSIGN;
 };
 
+// STAGED kernels: every thread keeps ST_D groups of ST_CH 128-bit vectors in flight as cp.async (LDGSTS) copies into its
+// OWN shared-memory slots (no cross-thread hazard, no barrier: cp.async.wait_group is per thread) and consumes the oldest
+// group with LDS.128 while the younger ones are still on their way.  The loads no longer sit in 32 staging registers and
+// the latency of a batch is hidden by the thread's own next batches instead of by other warps only.
+#ifndef ANV_ST_D
+#define ANV_ST_D 4
+#endif
+#ifndef ANV_ST_CH
+#define ANV_ST_CH 2
+#endif
+#ifndef ANV_FUSED_STAGED_DEFAULT
+#define ANV_FUSED_STAGED_DEFAULT 1
+#endif
+constexpr int ST_D = ANV_ST_D, ST_CH = ANV_ST_CH;
+constexpr size_t STAGE_BYTES = (size_t)ST_D * ST_CH * ANV_BLOCK * 16;
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+  return r;
+}
+
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
@@ -75,7 +104,7 @@ __device__ __forceinline__ void red_shared_inc(uint32_t saddr) {
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
 }
 
-enum BinMode { BIN_SEARCH = 0, BIN_GUESS = 1, BIN_CODE = 2 };
+enum BinMode { BIN_SEARCH = 0, BIN_GUESS = 1, BIN_CODE = 2, BIN_GUESS_FOLD = 3 };  // FOLD: device-side refinement of GUESS
 
 // ---- bin lookup -----------------------------------------------------------------------
 // S[0] = lowest, S[1..B-1] = thresholds theta_0..theta_{B-2}, S[B..P] = highest.
@@ -128,12 +157,18 @@ template <> __device__ __forceinline__ int Binner<double, BIN_GUESS>::slot(doubl
 //   a    = a0 + (x > th or unordered ? 1024 : 0)   => slot = r + !(x <= th)  (setp + predicated add)
 //   red.shared.add [a], 1                   NaN x: r' = 0, compare unordered => slot = B
 // FFMA.SAT saturates for free (no min/max clamp) and maps NaN to 0.
+// FOLD: when the range does not sit far from zero (fold_ok below), `x - lo` is folded into the multiply-add,
+//   v = sat(x * (-c) + k),  k = 1 + lo * c  (one instruction less per element).
+// The guess then carries the rounding errors of k and of c times |x| instead of |x - lo|: at most
+// (B-1) * 2^-23 * (2 + |lo| * c) bins, which fold_ok keeps below 1/32 - and ANY error below half a bin leaves the true
+// bin in {r-1, r}, which is all the exact threshold compare needs.
 struct FastF32 {
   uint32_t c_adj, toff;
-  float lo, negc, bm1;
-  __device__ __forceinline__ uint32_t counter_addr(float x) const {
+  float lo, negc, bm1, k;
+  template <bool FOLD> __device__ __forceinline__ uint32_t counter_addr(float x) const {
     float v;
-    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(v) : "f"(x - lo), "f"(negc), "f"(1.0f));
+    if (FOLD) asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(v) : "f"(x), "f"(negc), "f"(k));
+    else asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(v) : "f"(x - lo), "f"(negc), "f"(1.0f));
     const uint32_t bits = __float_as_uint(fmaf(v, bm1, 12582912.0f));
     uint32_t a = c_adj - (bits << 10);
     const float th = lds_f32(a + toff);
@@ -141,6 +176,12 @@ struct FastF32 {
     return a;
   }
 };
+
+// (B-1) * (2 + |lo| * c) <= 2^18  =>  guess error <= 2^-5 bins (c = inv_w / (B-1), so (B-1) * |lo| * c = |lo| * inv_w)
+__device__ __forceinline__ bool fold_ok(const anv_binspec_t& sp) {
+  const double e = 2.0 * (double)(sp.n_bins - 1) + fabs(sp.lo) * sp.inv_w;
+  return sp.n_bins >= 2 && e <= 262144.0;   // NaN / inf fail the compare
+}
 
 // n += (x != 0) as compare + predicated add (2 instructions; the C++ form costs a third, a select)
 template <typename T> __device__ __forceinline__ void count_nonzero(uint32_t& n, T x) { n += (x != (T)0) ? 1u : 0u; }
@@ -175,7 +216,7 @@ struct ScanShared {  // declared once in the kernel (not per template instantiat
 
 // ---- the tile body --------------------------------------------------------------------
 // HPATH: -1 no histogram, 0 private per-thread counters, 1 per-CTA shared atomics, 2 global atomics
-template <typename T, bool MOM, int HPATH, bool ASSIGN, bool NULLS, int MODE>
+template <typename T, bool MOM, int HPATH, bool ASSIGN, bool NULLS, int MODE, bool STAGED = false>
 __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_t& col, int c, unsigned char* smem,
                                           ScanShared& SS) {
   constexpr bool HIST = HPATH >= 0;
@@ -190,7 +231,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   const uint32_t* __restrict__ vwords = NULLS ? col.validity + (r0 >> 5) : nullptr;
 
   // ---- K2 setup: thresholds + counters in shared memory ------------------------------
-  Binner<T, MODE> bn;
+  Binner<T, (MODE == BIN_GUESS_FOLD ? (int)BIN_GUESS : MODE)> bn;
   uint32_t* cnt = nullptr;
   int n_slots = 0;
   if (HIST || ASSIGN) {
@@ -224,7 +265,9 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   }
   uint32_t* const cnt_t = cnt + tid;
   unsigned long long* const gcnt = P.counts + (size_t)c * P.count_stride;
-  constexpr bool FAST = HPATH == 0 && !ASSIGN && MODE == BIN_GUESS && sizeof(T) == 4;
+  constexpr bool GUESS = MODE == BIN_GUESS || MODE == BIN_GUESS_FOLD;
+  constexpr bool FAST = HPATH == 0 && !ASSIGN && GUESS && sizeof(T) == 4;
+  constexpr bool FOLD = MODE == BIN_GUESS_FOLD;
   FastF32 ff{};
   uint32_t cnt_t_saddr = 0;
   if (HPATH == 0) cnt_t_saddr = (uint32_t)__cvta_generic_to_shared(cnt_t);
@@ -235,6 +278,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
     for (int r = 0; r < bn.B; ++r) rep[r * ANV_BLOCK] = reinterpret_cast<const float*>(smem)[r];
     ff.c_adj = cnt_t_saddr + ((uint32_t)(bn.B - 1) << 10) + (0x4B400000u << 10);
     ff.lo = (float)bn.lo; ff.bm1 = (float)(bn.B - 1); ff.negc = -((float)bn.invw / ff.bm1);
+    ff.k = (float)(1.0 - (double)ff.lo * (double)ff.negc);
   }
 
   // ---- pivot = first finite non-null value among the tile's first rows ----------------------
@@ -275,7 +319,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
 
   double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
   T mn = Traits<T>::highest(), mx = Traits<T>::lowest();
-  uint32_t n_ok = 0, n_nz = 0, n_seen = 0;
+  uint32_t n_ok = 0, n_nz = 0;
   constexpr bool SLOT0 = ASSIGN || HPATH > 0;  // these paths need the literal slot 0 for null rows
 
   // x is already pivot-substituted on null lanes; `valid` is only consulted where slot 0 is needed
@@ -291,7 +335,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
       count_nonzero<T>(n_nz, x);
     }
     if (FAST) {
-      red_shared_inc(ff.counter_addr(*reinterpret_cast<const float*>(&x)));
+      red_shared_inc(ff.template counter_addr<FOLD>(*reinterpret_cast<const float*>(&x)));
     } else if (HIST || ASSIGN) {
       slot = bn.slot(x);
       if (NULLS && SLOT0) slot = valid ? slot : 0;
@@ -305,8 +349,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   };
   auto vec = [&](T (&e)[VEC], uint32_t vb, int (&sl)[VEC]) {
     if (NULLS) {
-      n_ok += __popc(vb);
-      n_seen += VEC;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) e[i] = ((vb >> i) & 1u) ? e[i] : pivot_t;
     }
@@ -332,7 +374,67 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   const uint4* __restrict__ vdata = reinterpret_cast<const uint4*>(data);
   const int vsh = (tid * VEC) & 31;  // bit offset of this thread's vector inside its bitmap word (loop-invariant)
   int base = 0;
-  if constexpr (Tune<MOM, HPATH, ASSIGN>::PF) {
+  if constexpr (STAGED) {
+  // thread-private cp.async ring: slot (s, u) of this thread at ring + ((s * ST_CH + u) * ANV_BLOCK) * 16 (+ tid * 16):
+  // consecutive lanes, consecutive 16 bytes - conflict-free for the copy-in and for LDS.128.  Same vector -> thread
+  // mapping as the register-staged loop (vector base + u * ANV_BLOCK + tid), so the per-thread sums are bit-identical.
+  constexpr int STEPV = ANV_BLOCK * ST_CH;  // vectors per group, CTA-wide
+  constexpr int WGRP = STEPV * VEC / 32;    // bitmap words per group
+  const int n_groups = nvec / STEPV;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem + P.stage_off) + (uint32_t)tid * 16u;
+  uint32_t vw[ST_D][ST_CH];  // raw validity words of the groups in flight (shifted / masked when consumed)
+  const uint4* pn = vdata + tid;                                             // next group to issue (running pointers:
+  const uint32_t* wn = NULLS ? vwords + ((tid * VEC) >> 5) : nullptr;        //  one 64-bit add per group)
+  auto issue = [&](int s) {
+#pragma unroll
+    for (int u = 0; u < ST_CH; ++u) {
+      cp_async16(ring + (uint32_t)((s * ST_CH + u) * ANV_BLOCK * 16), pn + u * ANV_BLOCK);
+      if (NULLS) vw[s][u] = __ldg(wn + u * WSTEP);
+    }
+    pn += STEPV;
+    if (NULLS) wn += WGRP;
+  };
+  auto consume = [&](int g, int s) {
+#pragma unroll
+    for (int u = 0; u < ST_CH; ++u) {
+      const uint4 q = lds_v4(ring + (uint32_t)((s * ST_CH + u) * ANV_BLOCK * 16));
+      T e[VEC];
+      unpack<T>(q, e);
+      int sl[VEC];
+      vec(e, NULLS ? ((vw[s][u] >> vsh) & VMASK) : VMASK, sl);
+      if (ASSIGN) store_bins((g * STEPV + u * ANV_BLOCK + tid) * VEC, sl);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < ST_D; ++s) {  // prologue: one commit per slot, empty when the tile is short (keeps the group count fixed)
+    if (s < n_groups) issue(s);
+    cp_async_commit();
+  }
+  int g0 = 0;
+  for (; g0 + 2 * ST_D <= n_groups; g0 += ST_D) {  // steady state: every slot is drained and refilled (conditions CTA-uniform)
+#pragma unroll
+    for (int s = 0; s < ST_D; ++s) {
+      cp_async_wait<ST_D - 1>();     // ST_D + g groups committed so far: group g = g0 + s has landed
+      consume(g0 + s, s);
+      issue(s);                      // refill the slot just drained (same thread, LSU order: the LDS is ahead of the copy)
+      cp_async_commit();
+    }
+  }
+  for (; g0 < n_groups; g0 += ST_D) {              // drain: at most 2 * ST_D - 1 groups left
+#pragma unroll
+    for (int s = 0; s < ST_D; ++s) {
+      const int g = g0 + s;
+      if (g < n_groups) {
+        cp_async_wait<ST_D - 1>();
+        consume(g, s);
+        if (g + ST_D < n_groups) issue(s);
+        cp_async_commit();
+      }
+    }
+  }
+  cp_async_wait<0>();
+  base = n_groups * STEPV;
+  } else if constexpr (Tune<MOM, HPATH, ASSIGN>::PF) {
   // software pipeline: the loads of batch k+1 are in flight while batch k is consumed
   constexpr int HB = UNROLL / 2;  // vectors per half batch
   constexpr int STEP = ANV_BLOCK * HB;
@@ -408,7 +510,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   if (tid == 0) {  // scalar tail (< VEC rows, last tile only)
     for (int row = nvec * VEC; row < n_tile; ++row) {
       bool valid = true;
-      if (NULLS) { valid = (vwords[row >> 5] >> (row & 31)) & 1u; n_ok += valid; n_seen += 1; }
+      if (NULLS) valid = (vwords[row >> 5] >> (row & 31)) & 1u;
       const T x = valid ? data[row] : pivot_t;
       if (MOM) { mn = min(mn, x); mx = max(mx, x); }
       const int sl = elem(x, valid);
@@ -417,7 +519,24 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   }
 
   // ---- undo the impersonation: this thread's null lanes were counted as pivot values --------
-  const uint32_t n_null = NULLS ? n_seen - n_ok : 0u;
+  // The streaming loop does not count valid lanes (that cost a mask, a POPC and two adds per vector): the tile's bitmap
+  // words are popcounted here instead, 32 rows per load, each thread its own share of the words.  The corrections only
+  // have to be right IN TOTAL over the CTA (the private counters and n_nz are summed over the threads afterwards), so every
+  // thread corrects by the nulls of the words IT popcounted, whichever lanes impersonated them; a thread's counter may
+  // wrap below zero on the way, the sums are taken modulo 2^32.
+  uint32_t n_null = 0u;
+  if (NULLS) {
+    const int nw = (n_tile + 31) >> 5;
+    uint32_t rows_cov = 0u;
+    for (int w = tid; w < nw; w += ANV_BLOCK) {
+      uint32_t v = __ldg(vwords + w);
+      const int left = n_tile - (w << 5);
+      if (left < 32) v &= (1u << left) - 1u;    // rows past the end of the frame
+      n_ok += __popc(v);
+      rows_cov += (uint32_t)min(left, 32);
+    }
+    n_null = rows_cov - n_ok;
+  }
   if (NULLS && MOM && pivot_t != (T)0) n_nz -= n_null;
   if (NULLS && HPATH == 0 && n_null) {
     const int sp = bn.slot(pivot_t);
@@ -470,13 +589,14 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
     __syncthreads();
     if (tid == 0) {
       double t1 = 0, t2 = 0, t3 = 0, t4 = 0, a = INFINITY, b = -INFINITY;
-      int64_t n = 0, nz = 0;
+      uint32_t n32 = 0, nz32 = 0;   // modulo 2^32: a warp's nonzero partial may have wrapped (null corrections, above)
 #pragma unroll
       for (int w = 0; w < ANV_WARPS; ++w) {  // fixed order: deterministic
         t1 += SS.red[w][0]; t2 += SS.red[w][1]; t3 += SS.red[w][2]; t4 += SS.red[w][3];
         a = fmin(a, SS.red[w][4]); b = fmax(b, SS.red[w][5]);
-        n += SS.redn[w][0]; nz += SS.redn[w][1];
+        n32 += SS.redn[w][0]; nz32 += SS.redn[w][1];
       }
+      const int64_t n = (int64_t)n32, nz = (int64_t)nz32;   // a tile holds <= 262144 rows
       Partial out;
       out.n = n; out.nz = nz; out.mn = a; out.mx = b;
       if (n > 0) {
@@ -525,7 +645,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
   }
 }
 
-template <bool MOM, int HPATH, bool ASSIGN>
+template <bool MOM, int HPATH, bool ASSIGN, bool STAGED = false>
 __global__ void __launch_bounds__(ANV_BLOCK, Tune<MOM, HPATH, ASSIGN>::MINB) scan_kernel(const ScanParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ ScanShared SS;
@@ -536,12 +656,16 @@ __global__ void __launch_bounds__(ANV_BLOCK, Tune<MOM, HPATH, ASSIGN>::MINB) sca
   if (BINS) mode = P.card ? BIN_CODE : P.specs[c].mode;
 #define ANV_TILE(T, MODE)                                                                   \
   do {                                                                                      \
-    if (col.validity) scan_tile<T, MOM, HPATH, ASSIGN, true, MODE>(P, col, c, smem, SS);    \
-    else scan_tile<T, MOM, HPATH, ASSIGN, false, MODE>(P, col, c, smem, SS);                \
+    if (col.validity) scan_tile<T, MOM, HPATH, ASSIGN, true, MODE, STAGED>(P, col, c, smem, SS);  \
+    else scan_tile<T, MOM, HPATH, ASSIGN, false, MODE, STAGED>(P, col, c, smem, SS);        \
   } while (0)
   switch (col.dtype) {
     case ANV_F32:
-      if (BINS && mode == BIN_GUESS) ANV_TILE(float, BIN_GUESS); else ANV_TILE(float, BIN_SEARCH);
+      if (BINS && mode == BIN_GUESS) {
+        // private-counter kernels: fold `x - lo` into the multiply-add when the guess stays within 1/32 bin (fold_ok)
+        if ((HPATH == 0 && !ASSIGN) && fold_ok(P.specs[c])) ANV_TILE(float, (HPATH == 0 && !ASSIGN) ? BIN_GUESS_FOLD : BIN_GUESS);
+        else ANV_TILE(float, BIN_GUESS);
+      } else ANV_TILE(float, BIN_SEARCH);
       break;
     case ANV_F64:
       if (BINS && mode == BIN_GUESS) ANV_TILE(double, BIN_GUESS); else ANV_TILE(double, BIN_SEARCH);
@@ -560,13 +684,20 @@ int pick_tile_rows(int64_t n_rows, int n_cols);
 size_t hist_smem(int count_stride, int* path, int* thr_slots, bool codes = false);
 int check_common(const void* cols, int n_cols, int64_t n_rows);
 
-template <bool MOM, int HPATH, bool ASSIGN>
+template <bool MOM, int HPATH, bool ASSIGN, bool STAGED = false>
 static int launch_scan(ScanParams& P, size_t smem, cudaStream_t st) {
   if (P.n_cols <= 0 || P.n_rows <= 0) return ANV_OK;
   dim3 grid((unsigned)((P.n_rows + P.tile_rows - 1) / P.tile_rows), (unsigned)P.n_cols);
+  if (STAGED) {  // the ring sits behind the counters, 16-byte aligned
+    P.stage_off = (uint32_t)((smem + 15) & ~(size_t)15);
+    smem = P.stage_off + STAGE_BYTES;
+    // four CTAs of (counters + ring) per SM need nearly all of the 228 KB: ask for the largest shared-memory carve-out
+    ANV_CUDA(cudaFuncSetAttribute(scan_kernel<MOM, HPATH, ASSIGN, STAGED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+  }
   if (smem > 40 * 1024)
-    ANV_CUDA(cudaFuncSetAttribute(scan_kernel<MOM, HPATH, ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scan_kernel<MOM, HPATH, ASSIGN><<<grid, ANV_BLOCK, smem, st>>>(P);
+    ANV_CUDA(cudaFuncSetAttribute(scan_kernel<MOM, HPATH, ASSIGN, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scan_kernel<MOM, HPATH, ASSIGN, STAGED><<<grid, ANV_BLOCK, smem, st>>>(P);
   ANV_CUDA(cudaGetLastError());
   return ANV_OK;
 }

@@ -410,3 +410,32 @@ def test_hll_registers_from_the_sorted_runs_equal_the_hll_kernel(n):
         res, _, regs = engine.sort_mode_distinct(fr, names, None, hll_p=p)
         assert res == engine.sort_mode_distinct(fr, names) or all(a[1:] == b[1:] for a, b in zip(res, engine.sort_mode_distinct(fr, names)))
         assert np.array_equal(regs, engine.hll_registers(fr, names, p)), p
+
+
+@pytest.mark.parametrize("n", [1, 1000, 2048 * 4 + 5, 300_001, 2_500_003])
+def test_fused_pass_staged_equals_register_staged(n, monkeypatch):
+    """The cp.async-staged fused moments + histogram kernel (default) against the register-staged one (ANV_FUSED_STAGED=0,
+    read per call): same vector -> thread mapping, so moments and counts are equal BIT FOR BIT; both equal the separate
+    moments and histogram kernels.  Sizes cover: no full group, drain only, steady state + drain, several tiles."""
+    from anovos_b200 import engine
+    from anovos_b200.frame import ColumnFrame
+    t = _mixed_table(n, seed=n % 97, null_rate=0.15).drop_columns(["f32_allnull"])
+    fr = ColumnFrame.from_arrow(t)
+    names = t.column_names
+    mom = engine.moments(fr, names)
+    cuts, lohi = [], []
+    for i, c in enumerate(names):
+        mn, mx = float(mom["min"][i]), float(mom["max"][i])
+        cuts.append(S.equal_range_cutoffs(mn, mx, 10))
+        lohi.append((mn, mx))
+    model = engine.BinModel(fr, names, cuts, lohi)
+    h = engine.histogram(fr, model)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ANV_FUSED_STAGED", flag)
+        out[flag] = engine.moments_histogram(fr, model)
+    (m0, h0), (m1, h1) = out["0"], out["1"]
+    assert (h0 == h1).all() and (h0 == h).all()
+    for f in engine.MOMENT_FIELDS:
+        assert np.array_equal(m0[f], m1[f], equal_nan=True), f
+        assert np.array_equal(mom[f], m1[f], equal_nan=True), f
