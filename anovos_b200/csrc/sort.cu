@@ -580,17 +580,21 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
     gbase[tid] = P.gbase[((size_t)c * sizeof(K) + P.pass) * 256 + tid] + (uint32_t)excl - ds_keep;
   }
   __syncthreads();
+  // the column's output base as ONE 64-bit register pair (opaque to the compiler: it otherwise re-derives
+  // c * stride + index in 64 bits for every key - 4 instructions per key of the copy-out)
+  K* outc = out;
+  asm volatile("" : "+l"(outc));
   if (FULL) {
 #pragma unroll
     for (int j = 0; j < SORT_TILE / SCAT_THREADS; ++j) {
       const int p = tid + j * SCAT_THREADS;
       const K k = sk[p];
-      out[(size_t)(gbase[digit_of(k, P.pass)] + (uint32_t)p)] = k;
+      outc[gbase[digit_of(k, P.pass)] + (uint32_t)p] = k;
     }
   } else {
     for (int p = tid; p < nt; p += SCAT_THREADS) {
       const K k = sk[p];
-      out[(size_t)(gbase[digit_of(k, P.pass)] + (uint32_t)p)] = k;
+      outc[gbase[digit_of(k, P.pass)] + (uint32_t)p] = k;
     }
   }
 }

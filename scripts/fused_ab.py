@@ -58,6 +58,38 @@ def run(flag):
     return float(np.median(ts)), float(np.min(ts)), out.cpu().numpy().tobytes(), counts.cpu().numpy().tobytes()
 
 
+def sustained(flag, launches=80):
+    """Enqueue `launches` back to back and sample NVML (SM clock, power, throttle reasons) while they run: the pass is
+    FP64- and HBM-heavy, and a B200 under its power cap lowers the SM clock within a few hundred milliseconds."""
+    import time
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+    os.environ["ANV_FUSED_STAGED"] = flag
+    out = torch.zeros(cols * 64, dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(cols * 11 * 8, dtype=torch.uint8, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(launches):
+        _lib.check(L.anv_moments_hist(desc.data_ptr(), specs.data_ptr(), dcuts.data_ptr(), cols, rows, out.data_ptr(),
+                                      counts.data_ptr(), 11, ws.data_ptr(), ws_bytes, st))
+    e1.record()
+    mhz, watts, reasons = [], [], set()
+    while not e1.query():
+        mhz.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+        watts.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for name in ("SwPowerCap", "HwSlowdown", "SwThermalSlowdown", "HwThermalSlowdown", "HwPowerBrakeSlowdown"):
+            if r & getattr(pynvml, "nvmlClocksThrottleReason" + name, 0):
+                reasons.add(name)
+        time.sleep(0.02)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / launches
+    return {"ms_per_launch": ms, "gbs": nbytes / ms / 1e6, "launches": launches, "sm_mhz_first": mhz[:3], "sm_mhz_median": float(np.median(mhz)) if mhz else None,
+            "sm_mhz_min": min(mhz) if mhz else None, "sm_mhz_max": pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM),
+            "power_w_max": max(watts) if watts else None, "reasons": sorted(reasons), "samples": len(mhz)}
+
+
 res = {}
 r0 = run("0"); r1 = run("1"); r0b = run("0"); r1b = run("1")
 peak = 6566.7
@@ -69,4 +101,10 @@ line = {"tag": tag, "rows": rows, "cols": cols, "nulls": null_mode, "bytes": nby
         "register_staged_ms": [r0[0], r0b[0]], "cp_async_staged_ms": [r1[0], r1b[0]],
         "register_staged_gbs": nbytes / min(r0[0], r0b[0]) / 1e6, "cp_async_staged_gbs": nbytes / min(r1[0], r1b[0]) / 1e6,
         "bit_identical": r0[2] == r1[2] and r0[3] == r1[3]}
+if os.environ.get("FUSED_AB_SUSTAINED", "1") != "0":
+    try:
+        line["sustained_default_loop"] = sustained("1")
+        line["sustained_register_staged"] = sustained("0")
+    except Exception as e:   # no NVML on the box: the burst numbers stand alone
+        line["sustained_error"] = repr(e)
 print(json.dumps(line))
