@@ -221,7 +221,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams& P, const anv_column_
                                           ScanShared& SS) {
   constexpr bool HIST = HPATH >= 0;
   constexpr int VEC = Traits<T>::VEC;
-  constexpr uint32_t VMASK = (1u << VEC) - 1u;
   constexpr int WSTEP = ANV_BLOCK * VEC / 32;  // bitmap words between two unrolled loads of a thread
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;

@@ -232,8 +232,99 @@ __device__ __forceinline__ void pack_tile(const SortParams<K>& P, const anv_colu
   __syncthreads();   // sk / s_warp are reused by the CTA's next tile
 }
 
+// Strided variant (ANV_PACK_STRIDED): thread t takes rows t, t + 256, ... of the tile (coalesced scalar loads, the bitmap
+// word of a warp's 32 rows is one broadcast load), a ballot per round ranks the surviving keys of the warp, and the staging
+// stores land on CONSECUTIVE shared-memory words per warp.  The contiguous variant above (16 consecutive rows per thread)
+// writes its staging stores 16 words apart - two banks per warp, 16-way conflicts (ncu: mio_throttle is its top stall).
+template <typename T> __device__ __forceinline__ T ld_stream_scalar(const T* p);
+template <> __device__ __forceinline__ float ld_stream_scalar<float>(const float* p) {
+  float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+}
+template <> __device__ __forceinline__ int32_t ld_stream_scalar<int32_t>(const int32_t* p) {
+  int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+template <> __device__ __forceinline__ double ld_stream_scalar<double>(const double* p) {
+  double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+}
+template <> __device__ __forceinline__ int64_t ld_stream_scalar<int64_t>(const int64_t* p) {
+  long long v; asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p)); return (int64_t)v;
+}
+
+template <typename K, typename T>
+__device__ __forceinline__ void pack_tile_strided(const SortParams<K>& P, const anv_column_t& col, int c, const int64_t tile, uint32_t* s_warp,
+                                                  unsigned long long* s_base, K* sk, uint32_t (*s_dh)[256]) {
+  constexpr int PER = SORT_TILE / ANV_BLOCK;        // 16 rounds of 256 rows
+  constexpr int WREG = SORT_TILE / ANV_WARPS;       // a warp stages at most 16 x 32 keys: its own 512 slots of sk
+  constexpr K ZERO_KEY = (K)1 << (sizeof(K) * 8 - 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = tile * SORT_TILE;              // multiple of 4096: the tile starts on a bitmap word
+  const int n_tile = (int)min((int64_t)SORT_TILE, P.n_rows - r0);
+  const T* __restrict__ data = reinterpret_cast<const T*>(col.data) + r0 + tid;
+  const uint32_t* __restrict__ vw = col.validity ? col.validity + (r0 >> 5) + warp : nullptr;   // round i: word i * 8 + warp, bit = lane
+  const uint32_t lbit = 1u << lane, lt = lbit - 1u;
+  K* const mine = sk + warp * WREG;
+  const bool full = n_tile == SORT_TILE;
+  T x[PER];
+  // the warp's 16 bitmap words (one per round), lane i holds round i's: one load per lane instead of 16 broadcast loads
+  uint32_t wv = ANV_FULL;
+  if (vw && lane < PER && (full || lane * ANV_BLOCK + warp * 32 < n_tile)) wv = __ldg(vw + lane * (ANV_BLOCK / 32));
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {                   // all loads of the tile in flight at once
+    const bool in = full || (i * ANV_BLOCK + tid) < n_tile;
+    x[i] = in ? ld_stream_scalar<T>(data + i * ANV_BLOCK) : (T)0;
+  }
+  uint32_t wcount = 0, nzero = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const K k = make_key<K, T>(x[i]);
+    bool ok = (__shfl_sync(ANV_FULL, wv, i) & lbit) != 0u;
+    if (!full) ok = ok && (i * ANV_BLOCK + tid) < n_tile;
+    const bool zero = ok && k == ZERO_KEY;          // 0.0 and -0.0 share one key; integers: 0
+    nzero += zero ? 1u : 0u;
+    ok = ok && !zero;
+    const uint32_t bal = __ballot_sync(ANV_FULL, ok);
+    if (ok) mine[wcount + __popc(bal & lt)] = k;    // consecutive lanes, consecutive words
+    wcount += __popc(bal);                          // warp-uniform
+  }
+  const uint32_t wz = __reduce_add_sync(ANV_FULL, nzero);
+  if (lane == 0 && wz) atomicAdd(&P.state[c].n_zero, (unsigned long long)wz);
+  if (lane == 0) s_warp[warp] = wcount;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t acc = 0;
+    for (int ww = 0; ww < ANV_WARPS; ++ww) { const uint32_t t = s_warp[ww]; s_warp[ww] = acc; acc += t; }
+    *s_base = acc ? atomicAdd(&P.state[c].n_valid, (unsigned long long)acc) : 0ull;
+  }
+  __syncthreads();
+  // every warp copies its own staged keys out (the order before a sort is irrelevant): contiguous, coalesced
+  K* __restrict__ out = P.buf[0] + (size_t)c * P.stride + *s_base + s_warp[warp];
+  if (P.ghist) {
+    for (uint32_t j = lane; j < wcount; j += 32) {
+      const K k = mine[j];
+      out[j] = k;
+#pragma unroll
+      for (int ps = 0; ps < (int)sizeof(K); ++ps) atomicAdd(&s_dh[ps][digit_of(k, ps)], 1u);
+    }
+  } else {
+    for (uint32_t j = lane; j < wcount; j += 32) out[j] = mine[j];
+  }
+  __syncthreads();   // sk / s_warp / s_base are reused by the CTA's next tile
+}
+
+#ifndef ANV_PACK_STRIDED
+#define ANV_PACK_STRIDED 0
+#endif
+#if ANV_PACK_STRIDED
+#define ANV_PACK_TILE pack_tile_strided
+#else
+#define ANV_PACK_TILE pack_tile
+#endif
+
+#ifndef ANV_PACK_MINB
+#define ANV_PACK_MINB 1
+#endif
 template <typename K>
-__global__ void __launch_bounds__(ANV_BLOCK) pack_kernel(const SortParams<K> P) {
+__global__ void __launch_bounds__(ANV_BLOCK, (sizeof(K) == 8 && ANV_PACK_MINB > 5) ? 5 : ANV_PACK_MINB) pack_kernel(const SortParams<K> P) {
   __shared__ uint32_t s_warp[ANV_WARPS];
   __shared__ unsigned long long s_base;
   __shared__ K sk[SORT_TILE];
@@ -247,10 +338,10 @@ __global__ void __launch_bounds__(ANV_BLOCK) pack_kernel(const SortParams<K> P) 
     const int64_t tile = (int64_t)blockIdx.x * PACK_TPC + t;
     if (tile * SORT_TILE >= P.n_rows) break;
     switch (col.dtype) {
-      case ANV_F32: pack_tile<K, float>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
-      case ANV_I32: pack_tile<K, int32_t>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
-      case ANV_F64: if (sizeof(K) == 8) pack_tile<K, double>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
-      case ANV_I64: if (sizeof(K) == 8) pack_tile<K, int64_t>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
+      case ANV_F32: ANV_PACK_TILE<K, float>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
+      case ANV_I32: ANV_PACK_TILE<K, int32_t>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
+      case ANV_F64: if (sizeof(K) == 8) ANV_PACK_TILE<K, double>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
+      case ANV_I64: if (sizeof(K) == 8) ANV_PACK_TILE<K, int64_t>(P, col, c, tile, s_warp, &s_base, sk, s_dh); break;
       default: break;
     }
   }
@@ -487,6 +578,10 @@ __device__ __noinline__ unsigned long long lookback_exclusive(volatile unsigned 
   return excl;
 }
 
+// store through the global window (the opaque base pointer below would otherwise compile to a generic ST)
+__device__ __forceinline__ void st_global_key(uint32_t* p, uint32_t v) { asm volatile("st.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_global_key(uint64_t* p, uint64_t v) { asm volatile("st.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
 template <typename K, bool FULL, bool LOOKBACK>
 __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColState& S, const int c, const int tile, const int64_t t0,
                                              const int nt_in, ScatShared<K>& SH) {
@@ -589,12 +684,12 @@ __device__ __forceinline__ void scatter_tile(const SortParams<K>& P, const ColSt
     for (int j = 0; j < SORT_TILE / SCAT_THREADS; ++j) {
       const int p = tid + j * SCAT_THREADS;
       const K k = sk[p];
-      outc[gbase[digit_of(k, P.pass)] + (uint32_t)p] = k;
+      st_global_key(outc + (gbase[digit_of(k, P.pass)] + (uint32_t)p), k);
     }
   } else {
     for (int p = tid; p < nt; p += SCAT_THREADS) {
       const K k = sk[p];
-      outc[gbase[digit_of(k, P.pass)] + (uint32_t)p] = k;
+      st_global_key(outc + (gbase[digit_of(k, P.pass)] + (uint32_t)p), k);
     }
   }
 }
