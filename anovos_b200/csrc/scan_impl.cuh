@@ -79,7 +79,7 @@ template <bool MOM, int HPATH, bool ASSIGN> struct Tune {
 #define ANV_ST_CH 2
 #endif
 #ifndef ANV_FUSED_STAGED_DEFAULT
-#define ANV_FUSED_STAGED_DEFAULT 1
+#define ANV_FUSED_STAGED_DEFAULT 0
 #endif
 constexpr int ST_D = ANV_ST_D, ST_CH = ANV_ST_CH;
 constexpr size_t STAGE_BYTES = (size_t)ST_D * ST_CH * ANV_BLOCK * 16;

@@ -876,8 +876,8 @@ def fused_pass_numbers(src, rows, names, peak, torch, engine):
         gbs = alg_bytes / (ms * 1e-3) / 1e9
         out[name] = {"ms_per_launch": ms, "algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
                      "rows_cols_per_s": rows * len(names) / (ms * 1e-3)}
-    out["fused"]["loop"] = ("null-free columns: 8 cp.async (LDGSTS) vectors per thread in flight through a thread-private shared-memory "
-                            "ring; columns with a validity bitmap: 8 x 128-bit loads in registers (ANV_FUSED_STAGED=0: registers everywhere)")
+    out["fused"]["loop"] = ("8 x 128-bit loads per thread in registers (default); ANV_FUSED_STAGED=1: null-free columns through a "
+                            "thread-private cp.async ring instead (A/B: profiles/r2b_fused_ab.md)")
     return out
 
 
