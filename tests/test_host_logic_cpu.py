@@ -2,6 +2,7 @@
 bit-identical.  CPU only (no kernel is launched)."""
 import numpy as np
 import pandas as pd
+import pytest
 
 from anovos_b200 import engine, parallel
 from anovos_b200.data_analyzer import stats_generator as sg
@@ -140,3 +141,61 @@ def test_result_frames_equal_the_plain_pandas_constructor():
             a.iloc[0, 0] = "changed"
             assert b.equals(exp) and rf.toPandas().equals(exp)
             assert rf.where({"attribute": cols["attribute"][0]}).count() == 1
+
+
+def _f32(x):
+    return np.float32(x)
+
+
+def _fma_f32(a, b, c):
+    """round-to-nearest float32 of a * b + c (a, b, c float32): the product is exact in float64 / longdouble."""
+    return np.float32(np.longdouble(np.float64(a) * np.float64(b)) + np.longdouble(c))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_folded_bin_guess_stays_within_one_bin_of_the_exact_slot(seed):
+    """NumPy restatement of the device's folded equal_range guess (csrc/scan_impl.cuh, FastF32::counter_addr<FOLD> and
+    fold_ok): v = sat(x * (-c) + k), k = 1 + lo * c, r' = round(v * (B-1)), r = B-1-r', slot = r + !(x <= S[r]).  The exact
+    threshold compare only repairs a guess that is at most one bin off, so the property to hold wherever fold_ok lets the
+    fold run is: the exact 0-based bin b = #(theta_i < x) lies in {r-1, r}.  Ranges at the edge of the fold_ok bound (|lo| / w
+    close to 2^18), values on and next to every threshold, the ends of the range, values outside it, NaN and infinities."""
+    from anovos_b200 import _lib, engine
+    rng = np.random.default_rng(seed)
+    checked = 0
+    for B in (2, 3, 10, 20, 39):
+        for ratio in (0.0, 1.0, 977.0, 2.0 ** 12, 2.0 ** 17, 2.0 ** 18 - 2.0 * (B - 1) - 1.0, -(2.0 ** 18 - 2.0 * (B - 1) - 1.0)):
+            w_target = float(rng.uniform(0.01, 50.0))
+            mn = float(np.float32(ratio * w_target))                   # |lo| / w ~ ratio
+            mx = float(np.float32(mn + B * w_target))
+            w = (mx - mn) / B
+            if not w > 0:
+                continue
+            cuts = [mn + j * w for j in range(1, B)]                   # the host's cutoffs (transformers.py:229-231)
+            theta = engine.native_thresholds(cuts, _lib.ANV_F32).astype(np.uint32).view(np.float32)
+            ulp = float(np.spacing(np.float32(max(abs(mn), abs(mx)))))
+            if not (np.all(np.diff(theta) > 0) and w >= 8 * ulp):      # BinModel's own condition for mode 1
+                continue
+            inv_w = 1.0 / w
+            if not (2.0 * (B - 1) + abs(mn) * inv_w <= 262144.0):      # fold_ok
+                continue
+            bm1 = _f32(B - 1)
+            negc = _f32(-(_f32(inv_w) / bm1))
+            lo = _f32(mn)
+            k = _f32(1.0 - float(lo) * float(negc))
+            xs = [theta, np.nextafter(theta, _f32(np.inf)), np.nextafter(theta, _f32(-np.inf)),
+                  np.array([mn, mx, np.nextafter(_f32(mn), _f32(np.inf)), np.nextafter(_f32(mx), _f32(-np.inf)),
+                            mn - 3 * w, mx + 3 * w, np.inf, -np.inf, np.nan], np.float32),
+                  rng.uniform(mn, mx, 2000).astype(np.float32)]
+            for x in np.concatenate(xs):
+                v = _fma_f32(x, negc, k)
+                v = _f32(0.0) if not v > 0 else min(v, _f32(1.0))      # .sat: NaN -> 0
+                t = _fma_f32(v, bm1, _f32(12582912.0))
+                r = (B - 1) - (int(np.float32(t).view(np.uint32)) - 0x4B400000)
+                assert 0 <= r <= B - 1
+                b = B - 1 if np.isnan(x) else int(np.sum(theta < x))   # bucket_label - 1; NaN: last bin
+                assert b in (r - 1, r), (B, ratio, float(x), r, b)
+                # what the kernel then does: one exact compare against S[r] (S[0] = NaN, S[r] = theta[r-1])
+                s_r = np.float32(np.nan) if r == 0 else theta[r - 1]
+                assert r + (0 if x <= s_r else 1) == b + 1
+                checked += 1
+    assert checked > 20000
