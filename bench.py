@@ -1061,7 +1061,7 @@ def cpu_baseline(cols, with_drift=False, rows=CPU_SAMPLE_ROWS, workers=None, cat
     t_stats, t_drift, used = cpu_bench.time_stats_generator(table, workers, target)
     out = {"value": rows * cols / t_stats, "unit": "rows*cols/s", "cores": used, "kind": "port",
            "sample": "the first %d rows of the SAME %d columns (bit-identical NumPy twin of the device generator), oracle (NumPy "
-                     "restatement of the Spark semantics, not Spark), one process per column group, %.2f s; rows*cols/s is "
+                     "restatement of the Spark semantics, not Spark), one column per task over all host cores, %.2f s; rows*cols/s is "
                      "extrapolated linearly in rows (the sorts are n log n: this favours the CPU)" % (rows, cols, t_stats),
            "host_cores": os.cpu_count()}
     if t_drift is not None:

@@ -63,25 +63,46 @@ def _split(names, k):
     return [names[i::k] for i in range(k)]
 
 
+def _all_cpus():
+    """Worker initializer: bench.py binds ITS process to the CPUs of the GPU's NUMA node (for the pinned buffers); the CPU
+    arm should use every host core the container allows, so the children widen their affinity again (best effort)."""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except (AttributeError, OSError, ValueError):
+        pass
+
+
+def _cost_order(table, names):
+    """Longest first (string columns cost about 3x a numeric one in the oracle): with one column per task and the idle
+    worker taking the next one, no worker is left holding two slow columns at the end."""
+    import pyarrow as pa
+    slow = [n for n in names if pa.types.is_string(table.schema.field(n).type) or pa.types.is_large_string(table.schema.field(n).type)
+            or pa.types.is_dictionary(table.schema.field(n).type)]
+    slow_set = set(slow)
+    return slow + [n for n in names if n not in slow_set]
+
+
 def time_stats_generator(table, workers=None, target=None):
     """Wall seconds of the 6 measures_of_* functions (+ drift when `target` is given) over
-    `table`, columns spread over `workers` processes (fork: the table is shared, not pickled)."""
+    `table`: one column per task, handed to `workers` processes as they become free (fork: the table is shared, not pickled)."""
     global _TABLE, _TARGET
     _TABLE, _TARGET = table, target
-    workers = workers or os.cpu_count() or 1
-    groups = _split(table.column_names, workers)
+    workers = max(1, min(workers or os.cpu_count() or 1, len(table.column_names)))
+    tasks = [[n] for n in _cost_order(table, table.column_names)]
     ctx = mp.get_context("fork")
-    with ctx.Pool(len(groups)) as pool:
-        pool.map(_stats_group, [g[:1] for g in groups])  # warm the workers (imports), not timed
+    with ctx.Pool(workers, initializer=_all_cpus) as pool:
+        pool.map(_stats_group, [t for t in tasks[:workers]], chunksize=1)  # warm the workers (imports), not timed
         t0 = time.perf_counter()
-        pool.map(_stats_group, groups)
+        for _ in pool.imap_unordered(_stats_group, tasks, chunksize=1):
+            pass
         t_stats = time.perf_counter() - t0
         t_drift = None
         if target is not None:
             t0 = time.perf_counter()
-            pool.map(_drift_group, groups)
+            for _ in pool.imap_unordered(_drift_group, tasks, chunksize=1):
+                pass
             t_drift = time.perf_counter() - t0
-    return t_stats, t_drift, len(groups)
+    return t_stats, t_drift, workers
 
 
 # ---- parity leg of bench.py: the oracle's answers for a few columns of the bench frame at full length ---------------
