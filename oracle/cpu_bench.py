@@ -46,21 +46,17 @@ def _stream_group(names):
 
 
 def time_stream_step(table, target, workers=None):
-    """Wall seconds of the streamed step over (table, target), columns spread over `workers` processes."""
+    """Wall seconds of the streamed step over (table, target), one column per task over `workers` processes."""
     global _TABLE, _TARGET
     _TABLE, _TARGET = table, target
-    workers = workers or os.cpu_count() or 1
-    groups = _split(table.column_names, workers)
-    with mp.get_context("fork").Pool(len(groups)) as pool:
-        pool.map(_stats_group, [g[:1] for g in groups])  # warm the workers (imports), not timed
+    workers = max(1, min(workers or os.cpu_count() or 1, len(table.column_names)))
+    tasks = [[n] for n in _cost_order(table, table.column_names)]
+    with mp.get_context("fork").Pool(workers, initializer=_all_cpus) as pool:
+        pool.map(_stats_group, tasks[:workers], chunksize=1)  # warm the workers (imports), not timed
         t0 = time.perf_counter()
-        pool.map(_stream_group, groups)
-        return time.perf_counter() - t0, len(groups)
-
-
-def _split(names, k):
-    k = max(1, min(k, len(names)))
-    return [names[i::k] for i in range(k)]
+        for _ in pool.imap_unordered(_stream_group, tasks, chunksize=1):
+            pass
+        return time.perf_counter() - t0, workers
 
 
 def _all_cpus():
