@@ -2,8 +2,9 @@
 // scan_mom.cu / scan_hist.cu / scan_fused.cu / scan_assign.cu so nvcc compiles them in parallel).
 //
 // One CTA handles one (column, row-tile): it streams the tile with 128-bit no-allocate
-// loads (coalesced: consecutive threads read consecutive 16 B, 4 loads in flight per
-// thread, immediate offsets, 32-bit in-tile indexing) and keeps
+// loads (coalesced: consecutive threads read consecutive 16 B, 8 loads in flight per
+// thread, immediate offsets, 32-bit in-tile indexing; an opt-in second instantiation of the fused
+// kernel stages null-free columns through a thread-private cp.async ring instead) and keeps
 //   K1  count / nonzero / min / max in native-type lanes and the pivot-shifted power sums
 //       sum d, d^2, d^3, d^4 (d = double(x) - pivot) in FP64 registers;
 //   K2  the bin id from ONE fused multiply-add guess fixed up by ONE exact native-type
